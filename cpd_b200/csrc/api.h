@@ -1,0 +1,96 @@
+// api.h — torch-free C++ entry points of the native library (CPU ops, CUDA
+// launchers, comm runtime).  bindings.cpp is the only file that sees PyTorch.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#ifndef CPD_NO_CUDA
+#include <cuda_runtime.h>
+#else
+typedef void* cudaStream_t;
+#endif
+
+namespace cpd {
+
+// One schedulable piece of a flat multi-tensor arena: `len` elements starting at
+// `start`, all inside tensor `tensor` (so one APS shift / one trust ratio applies).
+struct Chunk {
+  long long start;
+  int len;
+  int tensor;
+};
+
+// ------------------------------------------------------------------ CPU ops --
+void quantize_cpu(const float* in, float* out, int64_t n, int e, int m, int rounding);
+void quantize_scaled_cpu(const float* in, float* out, int64_t n, int e, int m, int rounding, int shift);
+// C[M,N] = A[M,K] * B[K,N]; per-MAC quantised (optionally Kahan) sequential-k accumulation
+// A(i,k) = A[i*sa0 + k*sa1], B(k,j) = B[k*sb0 + j*sb1]  (strides express transposes)
+void gemm_exact_cpu(const float* A, int64_t sa0, int64_t sa1, const float* B, int64_t sb0, int64_t sb1,
+                    float* C, int64_t ldc, int M, int N, int K, int e, int m, int rounding, bool kahan);
+// tile semantics: fp32 partial over each K-slice (operands optionally pre-rounded to
+// an operand format), then s = Q(s (+) Q(partial)) per slice.
+void gemm_tile_cpu(const float* A, int64_t sa0, int64_t sa1, const float* B, int64_t sb0, int64_t sb1,
+                   float* C, int64_t ldc, int M, int N, int K, int e, int m, int rounding, bool kahan,
+                   int k_slice, int op_e, int op_m);
+// APS + rank-ordered (Kahan) fold over W source buffers that share one segment table.
+void aps_fold_cpu(const float* const* srcs, int W, float* out, const int64_t* seg_off, int T,
+                  int e, int m, int rounding, bool use_aps, bool kahan, float world_mult,
+                  int* shifts_out);
+// LARS / SGD multi-tensor step on fp32 masters (reference mix.py:297-314 semantics).
+void lars_step_cpu(float* master, float* model, const float* grad, float* mom, const int64_t* seg_off,
+                   int T, float lr, float momentum, float wd, float coeff, float eps, bool use_lars,
+                   bool nesterov, const float* wd_mult);
+
+// ----------------------------------------------------------------- CUDA ops --
+#ifndef CPD_NO_CUDA
+int device_sm_count(int dev);
+
+void quantize_cuda(const float* in, float* out, int64_t n, int e, int m, int rounding, int shift,
+                   cudaStream_t st);
+// fused amax + quantize statistics (optional): writes |x| max bits into *amax_bits
+void amax_cuda(const float* in, int64_t n, unsigned* amax_bits, cudaStream_t st);
+
+void gemm_exact_cuda(const float* A, int64_t sa0, int64_t sa1, const float* B, int64_t sb0, int64_t sb1,
+                     float* C, int64_t ldc, int M, int N, int K, int e, int m, int rounding, bool kahan,
+                     cudaStream_t st);
+
+// Multi-source APS fold (local sources: emulate_node slots, or W==1): one launch.
+//   srcs: device array of W pointers to flat fp32 arenas sharing the chunk table
+//   workspace: 4 + 2*T_cap unsigned (grid barrier, launch counter, amax[2][T_cap]), zeroed once
+void aps_fold_local_cuda(const float* const* srcs, int W, float* out, const Chunk* chunks,
+                         int n_chunks, int T, int T_cap, int e, int m, bool use_aps, bool kahan,
+                         float world_mult, unsigned* workspace, int* shifts_out, int max_ctas,
+                         cudaStream_t st);
+
+void lars_step_cuda(float* master, float* model, const float* grad, float* mom, const Chunk* chunks,
+                    const int* tchunk_off, int n_chunks, int T, const float* lr_dev, float lr,
+                    float momentum, float wd, float coeff, float eps, bool use_lars, bool nesterov,
+                    const float* wd_mult, float* partials, unsigned* barrier_ws, int max_ctas,
+                    cudaStream_t st);
+
+// Cross-GPU fused all-reduce over peer memory.  See cuda/allreduce_fused_sm100a.cu.
+struct CommBuffers {
+  int rank, world;
+  // per-rank device pointers into the symmetric region (index = rank)
+  unsigned char* data[16];     // wire buffers   [2][cap_bytes]
+  unsigned char* gather[16];   // reduced-slice buffers [2][cap_bytes]
+  float* mailbox[16];          // APS exponents  [2][max_tensors]
+  unsigned* flags[16];         // signal pad     [3][16] epoch flags per phase
+  unsigned char* mc_gather;    // multicast view of `gather` (nullptr when no NVLS)
+  size_t cap_bytes;
+  int max_tensors;
+};
+enum AllreduceAlgo : int { ALGO_AUTO = 0, ALGO_ONESHOT = 1, ALGO_TWOSHOT = 2, ALGO_NVLS = 3 };
+void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunks, int n_chunks,
+                          int T, int e, int m, bool use_aps, bool kahan, int algo, bool prequant, int wire,
+                          unsigned* local_ws /*barrier[2], epoch, status, amax[2][T]*/, int* shifts_out,
+                          int max_ctas, unsigned long long timeout_cycles, cudaStream_t st);
+
+// tcgen05 / TMEM / TMA GEMM with per-K-slice accumulator re-quantisation.
+// operand_mode: 0 = bf16 operands (kind::f16), 1 = tf32 (kind::tf32), 2 = e4m3, 3 = e5m2
+int gemm_tc_cuda(const void* A, const void* B, float* C, int M, int N, int K, int e, int m,
+                 bool kahan, int k_slice, int operand_mode, const float* bias, cudaStream_t st);
+#endif
+
+}  // namespace cpd

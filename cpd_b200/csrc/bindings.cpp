@@ -1,0 +1,190 @@
+// bindings.cpp — python module cpd_b200._C.
+//
+// Deliberately torch-free: every entry point takes raw device/host addresses
+// (tensor.data_ptr()), sizes and the CUDA stream handle as integers; shape, dtype,
+// device and contiguity validation lives in cpd_b200/ops/native.py.  This keeps the
+// native library independent of libtorch's C++ ABI (it links only the CUDA runtime)
+// and makes it usable from any framework that can hand out pointers.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <stdexcept>
+
+#include "api.h"
+#include "comm/comm.h"
+#include "common/fpformat.h"
+
+namespace py = pybind11;
+using uptr = uintptr_t;
+
+namespace {
+
+template <class T> T* P(uptr p) { return reinterpret_cast<T*>(p); }
+cudaStream_t S(uptr s) { return reinterpret_cast<cudaStream_t>(s); }
+
+void check_fmt(int e, int m) {
+  if (e < 1 || e > 8) throw std::invalid_argument("exp must be in [1, 8]");
+  if (m < 0 || m > 23) throw std::invalid_argument("man must be in [0, 23]");
+}
+void check_launch(const char* what) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) throw std::runtime_error(std::string("cpd_b200: ") + what + " launch failed: " + cudaGetErrorString(err));
+}
+
+struct PyCommBuffers { cpd::CommBuffers cb; };
+
+}  // namespace
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "cpd_b200 native ops (sm_100a CUDA kernels, C++ CPU reference paths, comm runtime)";
+
+  // ---------------------------------------------------------------- elementwise --
+  m.def("quantize_cpu", [](uptr in, uptr out, int64_t n, int e, int mb, int rounding, int shift) {
+    check_fmt(e, mb);
+    py::gil_scoped_release nogil;
+    if (shift == 0) cpd::quantize_cpu(P<const float>(in), P<float>(out), n, e, mb, rounding);
+    else cpd::quantize_scaled_cpu(P<const float>(in), P<float>(out), n, e, mb, rounding, shift);
+  });
+  m.def("quantize_cuda", [](uptr in, uptr out, int64_t n, int e, int mb, int rounding, int shift, uptr stream) {
+    check_fmt(e, mb);
+    cpd::quantize_cuda(P<const float>(in), P<float>(out), n, e, mb, rounding, shift, S(stream));
+    check_launch("quantize");
+  });
+  m.def("amax_cuda", [](uptr in, int64_t n, uptr amax_bits, uptr stream) {
+    cpd::amax_cuda(P<const float>(in), n, P<unsigned>(amax_bits), S(stream));
+    check_launch("amax");
+  });
+
+  // ----------------------------------------------------------------------- GEMM --
+  m.def("gemm_exact_cpu", [](uptr A, int64_t sa0, int64_t sa1, uptr B, int64_t sb0, int64_t sb1, uptr C, int64_t ldc, int M,
+                             int N, int K, int e, int mb, int rounding, bool kahan) {
+    check_fmt(e, mb);
+    py::gil_scoped_release nogil;
+    cpd::gemm_exact_cpu(P<const float>(A), sa0, sa1, P<const float>(B), sb0, sb1, P<float>(C), ldc, M, N, K, e, mb, rounding, kahan);
+  });
+  m.def("gemm_tile_cpu", [](uptr A, int64_t sa0, int64_t sa1, uptr B, int64_t sb0, int64_t sb1, uptr C, int64_t ldc, int M,
+                            int N, int K, int e, int mb, int rounding, bool kahan, int k_slice, int op_e, int op_m) {
+    check_fmt(e, mb);
+    py::gil_scoped_release nogil;
+    cpd::gemm_tile_cpu(P<const float>(A), sa0, sa1, P<const float>(B), sb0, sb1, P<float>(C), ldc, M, N, K, e, mb, rounding, kahan,
+                       k_slice, op_e, op_m);
+  });
+  m.def("gemm_exact_cuda", [](uptr A, int64_t sa0, int64_t sa1, uptr B, int64_t sb0, int64_t sb1, uptr C, int64_t ldc, int M,
+                              int N, int K, int e, int mb, int rounding, bool kahan, uptr stream) {
+    check_fmt(e, mb);
+    cpd::gemm_exact_cuda(P<const float>(A), sa0, sa1, P<const float>(B), sb0, sb1, P<float>(C), ldc, M, N, K, e, mb, rounding,
+                         kahan, S(stream));
+    check_launch("gemm_exact");
+  });
+  // A [M,K] row-major, Bt [N,K] row-major (both K-major); operand_mode 0 bf16, 1 tf32(fp32 in), 2 e4m3, 3 e5m2
+  m.def("gemm_tc_cuda", [](uptr A, uptr Bt, uptr C, int M, int N, int K, int e, int mb, bool kahan, int k_slice,
+                           int operand_mode, uptr bias, uptr stream) {
+    check_fmt(e, mb);
+    int rc = cpd::gemm_tc_cuda(P<const void>(A), P<const void>(Bt), P<float>(C), M, N, K, e, mb, kahan, k_slice, operand_mode,
+                               P<const float>(bias), S(stream));
+    check_launch("gemm_tc");
+    return rc;
+  });
+
+  // --------------------------------------------------------- multi-tensor arenas --
+  m.def("aps_fold_cpu", [](std::vector<uptr> srcs, uptr out, uptr seg_off, int T, int e, int mb, bool use_aps, bool kahan,
+                           double world_mult, uptr shifts_out) {
+    check_fmt(e, mb);
+    std::vector<const float*> ptrs;
+    for (auto s : srcs) ptrs.push_back(P<const float>(s));
+    py::gil_scoped_release nogil;
+    cpd::aps_fold_cpu(ptrs.data(), (int)ptrs.size(), P<float>(out), P<const int64_t>(seg_off), T, e, mb, cpd::ROUND_REF, use_aps,
+                      kahan, (float)world_mult, P<int>(shifts_out));
+  });
+  m.def("aps_fold_cuda", [](std::vector<uptr> srcs, uptr out, uptr chunks, int n_chunks, int T, int T_cap, int e, int mb, bool use_aps,
+                            bool kahan, double world_mult, uptr workspace, uptr shifts_out, int max_ctas, uptr stream) {
+    check_fmt(e, mb);
+    if (srcs.empty() || srcs.size() > 16) throw std::invalid_argument("aps_fold: 1..16 sources");
+    std::vector<const float*> ptrs;
+    for (auto s : srcs) ptrs.push_back(P<const float>(s));
+    cpd::aps_fold_local_cuda(ptrs.data(), (int)ptrs.size(), P<float>(out), P<const cpd::Chunk>(chunks), n_chunks, T, T_cap, e, mb, use_aps,
+                             kahan, (float)world_mult, P<unsigned>(workspace), P<int>(shifts_out), max_ctas, S(stream));
+    check_launch("aps_fold");
+  });
+  m.def("lars_step_cpu", [](uptr master, uptr model, uptr grad, uptr mom, uptr seg_off, int T, double lr, double momentum,
+                            double wd, double coeff, double eps, bool use_lars, bool nesterov, uptr wd_mult) {
+    py::gil_scoped_release nogil;
+    cpd::lars_step_cpu(P<float>(master), P<float>(model), P<const float>(grad), P<float>(mom), P<const int64_t>(seg_off), T,
+                       (float)lr, (float)momentum, (float)wd, (float)coeff, (float)eps, use_lars, nesterov, P<const float>(wd_mult));
+  });
+  m.def("lars_step_cuda", [](uptr master, uptr model, uptr grad, uptr mom, uptr chunks, uptr tchunk_off, int n_chunks, int T,
+                             uptr lr_dev, double lr, double momentum, double wd, double coeff, double eps, bool use_lars,
+                             bool nesterov, uptr wd_mult, uptr partials, uptr barrier_ws, int max_ctas, uptr stream) {
+    cpd::lars_step_cuda(P<float>(master), P<float>(model), P<const float>(grad), P<float>(mom), P<const cpd::Chunk>(chunks),
+                        P<const int>(tchunk_off), n_chunks, T, P<const float>(lr_dev), (float)lr, (float)momentum, (float)wd,
+                        (float)coeff, (float)eps, use_lars, nesterov, P<const float>(wd_mult), P<float>(partials),
+                        P<unsigned>(barrier_ws), max_ctas, S(stream));
+    check_launch("lars_step");
+  });
+
+  // ------------------------------------------------------------------ wire codec --
+  m.def("wire_roundtrip_cpu", [](uptr in, uptr out, int64_t n, int e, int mb) {
+    const float* p = P<const float>(in);
+    float* o = P<float>(out);
+    for (int64_t i = 0; i < n; ++i) o[i] = cpd::wire_unpack(cpd::wire_pack(p[i], e, cpd::wire_man(mb)), e, cpd::wire_man(mb));
+  });
+  m.def("wire_bits", [](int e, int mb) { return cpd::wire_bits(e, mb); });
+  m.def("chunk_struct_size", []() { return (int)sizeof(cpd::Chunk); });
+  m.def("sm_count", [](int dev) { return cpd::device_sm_count(dev); });
+
+  // ------------------------------------------------------------------------ comm --
+  m.def("discover_topology_json", &cpd::comm::discover_topology_json);
+
+  py::class_<cpd::comm::SymmRegion>(m, "SymmRegion")
+      .def(py::init<size_t, int, int, int, const std::string&, bool>())
+      .def("open", &cpd::comm::SymmRegion::open, py::call_guard<py::gil_scoped_release>())
+      .def("exchange", &cpd::comm::SymmRegion::exchange, py::call_guard<py::gil_scoped_release>())
+      .def("bind_multicast", &cpd::comm::SymmRegion::bind_multicast, py::call_guard<py::gil_scoped_release>())
+      .def("ptr", [](const cpd::comm::SymmRegion& r, int i) { return reinterpret_cast<uptr>(r.ptr(i)); })
+      .def("mc_ptr", [](const cpd::comm::SymmRegion& r) { return reinterpret_cast<uptr>(r.mc_ptr()); })
+      .def("bytes", &cpd::comm::SymmRegion::bytes)
+      .def("log", &cpd::comm::SymmRegion::log);
+
+  m.def("ipc_alloc", [](size_t bytes) { return reinterpret_cast<uptr>(cpd::comm::IpcRegion::alloc(bytes)); });
+  m.def("ipc_export", [](uptr p) { return py::bytes(cpd::comm::IpcRegion::export_handle(P<void>(p))); });
+  m.def("ipc_open", [](const std::string& h) { return reinterpret_cast<uptr>(cpd::comm::IpcRegion::open_handle(h)); });
+  m.def("ipc_close", [](uptr p) { cpd::comm::IpcRegion::close_handle(P<void>(p)); });
+  m.def("ipc_free", [](uptr p) { cpd::comm::IpcRegion::free_local(P<void>(p)); });
+
+  py::class_<PyCommBuffers>(m, "CommBuffers")
+      .def(py::init([](int rank, int world, std::vector<uptr> data, std::vector<uptr> gather, std::vector<uptr> mailbox,
+                       std::vector<uptr> flags, uptr mc_gather, size_t cap_bytes, int max_tensors) {
+        if (world < 1 || world > 8) throw std::invalid_argument("fused all-reduce supports 1..8 ranks per node");
+        if ((int)data.size() != world || (int)gather.size() != world || (int)mailbox.size() != world || (int)flags.size() != world)
+          throw std::invalid_argument("CommBuffers: need one pointer per rank");
+        PyCommBuffers b;
+        b.cb.rank = rank; b.cb.world = world;
+        for (int r = 0; r < 16; ++r) { b.cb.data[r] = nullptr; b.cb.gather[r] = nullptr; b.cb.mailbox[r] = nullptr; b.cb.flags[r] = nullptr; }
+        for (int r = 0; r < world; ++r) {
+          b.cb.data[r] = P<unsigned char>(data[r]);
+          b.cb.gather[r] = P<unsigned char>(gather[r]);
+          b.cb.mailbox[r] = P<float>(mailbox[r]);
+          b.cb.flags[r] = P<unsigned>(flags[r]);
+        }
+        b.cb.mc_gather = P<unsigned char>(mc_gather);
+        b.cb.cap_bytes = cap_bytes;
+        b.cb.max_tensors = max_tensors;
+        return b;
+      }))
+      .def_property_readonly("cap_bytes", [](const PyCommBuffers& b) { return b.cb.cap_bytes; })
+      .def_property_readonly("max_tensors", [](const PyCommBuffers& b) { return b.cb.max_tensors; })
+      .def_property_readonly("has_multicast", [](const PyCommBuffers& b) { return b.cb.mc_gather != nullptr; });
+
+  m.def("allreduce_fused_cuda", [](const PyCommBuffers& b, uptr grad, int64_t numel, uptr chunks, int n_chunks, int T, int e, int mb,
+                                   bool use_aps, bool kahan, int algo, bool prequant, int wire, uptr local_ws, uptr shifts_out,
+                                   int max_ctas, uint64_t timeout_cycles, uptr stream) {
+    check_fmt(e, mb);
+    if (T > 1024) throw std::invalid_argument("at most 1024 tensors per bucket");
+    if (T > b.cb.max_tensors) throw std::invalid_argument("bucket has more tensors than the mailbox holds");
+    if (wire != 8 && wire != 16 && wire != 32) throw std::invalid_argument("wire must be 8, 16 or 32");
+    if ((size_t)numel * (size_t)(wire / 8) > b.cb.cap_bytes) throw std::invalid_argument("bucket larger than the symmetric wire buffer");
+    cpd::allreduce_fused_cuda(b.cb, P<float>(grad), P<const cpd::Chunk>(chunks), n_chunks, T, e, mb, use_aps, kahan, algo, prequant,
+                              wire, P<unsigned>(local_ws), P<int>(shifts_out), max_ctas, timeout_cycles, S(stream));
+    check_launch("allreduce_fused");
+  });
+}

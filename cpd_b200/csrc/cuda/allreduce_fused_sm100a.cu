@@ -1,0 +1,380 @@
+// allreduce_fused_sm100a.cu — the data-parallel gradient all-reduce of CPD as ONE
+// sm_100a kernel per bucket, over NVSwitch peer memory.
+//
+// Reference path being replaced (CPDtorch/utils/dist_util.py:22-89): per parameter
+// {abs, mul, max, log2, ceil} + host syncs + NCCL all_reduce(MAX) + scale +
+// float_quantize + NCCL all_gather of fp32 + W x {add, memset, quantize} (or
+// 4 quantizes + 4 add/sub for Kahan) + unscale: ~46 launches, 2 collectives and
+// >= 2 host syncs per parameter, fp32 on the wire ((W-1)*4 B per element in).
+//
+// This kernel fuses all of it for a whole bucket (many tensors, per-tensor shift):
+//   A  per-tensor max|g|                      -> grid barrier -> exponent to own mailbox,
+//      signal peers; wait peers; shift[t] = bias - max_r ceil(log2(amax_r * W))
+//   B  g -> Q(g * 2^shift) -> packed wire code (8/16/32 bit) into own symmetric
+//      buffer                                  -> grid barrier -> signal peers; wait peers
+//   C  one-shot : every rank loads all W peers' codes (128-bit peer loads over
+//                 NVLink), folds in rank order with a cast after every add (Kahan:
+//                 (res, c) in registers), unscales, stores fp32 gradients.
+//      two-shot : rank r folds only the chunks it owns, stores the fp32 result
+//                 locally and pushes the packed reduced codes into every peer's
+//                 gather buffer (P2P stores, or ONE multimem.st through the NVLS
+//                 multicast mapping) -> grid barrier -> signal; wait -> every rank
+//                 unpacks + unscales the chunks it does not own.
+// Every rank folds in the same rank order, so results are bit-identical on all
+// ranks and equal to the reference semantics.  Buffers and
+// mailboxes are double-buffered by epoch parity and flags are monotonic epochs, so
+// no trailing barrier and no host-side reset is needed (CUDA-graph replay safe).
+#include "../api.h"
+#include "../common/fpformat.h"
+#include "../common/device_utils.cuh"
+#include "format_dispatch.cuh"
+
+namespace cpd {
+
+constexpr int kArThreads = 256;
+constexpr int kArMaxW = 8;
+constexpr int kArMaxT = 1024;       // tensors per bucket (shifts live in shared memory)
+constexpr int kFlagStride = 16;     // flags[phase][src]
+
+struct ArParams {
+  int rank, world;
+  unsigned char* data[kArMaxW];
+  unsigned char* gather[kArMaxW];
+  float* mailbox[kArMaxW];
+  unsigned* flags[kArMaxW];
+  unsigned char* mc_gather;
+  long long cap_bytes;
+  int max_tensors;
+  float* grad;
+  const Chunk* chunks;
+  int n_chunks, T;
+  int use_aps, algo, prequant, ident;
+  unsigned* ws;          // [0],[1] grid barrier; [2] epoch; [3] status; [4..4+2*max_tensors) amax[2][max_tensors]
+  int* shifts_out;
+  unsigned long long timeout;
+};
+
+// ---- wire granule (16 elements) load / store / codec ------------------------------
+template <int WIRE> struct Granule;
+template <> struct Granule<8> { uint4 v[1]; };
+template <> struct Granule<16> { uint4 v[2]; };
+template <> struct Granule<32> { uint4 v[4]; };
+
+template <int WIRE>
+__device__ __forceinline__ Granule<WIRE> granule_load_sys(const unsigned char* base, long long elem) {
+  Granule<WIRE> g;
+  const unsigned char* p = base + elem * (WIRE / 8);
+#pragma unroll
+  for (int i = 0; i < WIRE / 8; ++i) g.v[i] = ld_sys_u4(p + 16 * i);
+  return g;
+}
+template <int WIRE>
+__device__ __forceinline__ void granule_store(unsigned char* base, long long elem, const Granule<WIRE>& g, bool sys) {
+  unsigned char* p = base + elem * (WIRE / 8);
+#pragma unroll
+  for (int i = 0; i < WIRE / 8; ++i) {
+    if (sys) st_sys_u4(p + 16 * i, g.v[i]);
+    else st_u4(p + 16 * i, g.v[i]);
+  }
+}
+template <int WIRE>
+__device__ __forceinline__ void granule_store_mc(unsigned char* mc_base, long long elem, const Granule<WIRE>& g) {
+  unsigned char* p = mc_base + elem * (WIRE / 8);
+#pragma unroll
+  for (int i = 0; i < WIRE / 8; ++i) multimem_st_u4(p + 16 * i, g.v[i]);
+}
+
+template <int WIRE, class F>
+__device__ __forceinline__ void granule_decode(const F& fmt, const Granule<WIRE>& g, float (&x)[16]) {
+  if (WIRE == 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      x[4 * i + 0] = __uint_as_float(g.v[i].x); x[4 * i + 1] = __uint_as_float(g.v[i].y);
+      x[4 * i + 2] = __uint_as_float(g.v[i].z); x[4 * i + 3] = __uint_as_float(g.v[i].w);
+    }
+  } else if (WIRE == 16) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const unsigned w[4] = {g.v[i].x, g.v[i].y, g.v[i].z, g.v[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        x[8 * i + 2 * k] = fmt.unpack(w[k] & 0xFFFFu);
+        x[8 * i + 2 * k + 1] = fmt.unpack(w[k] >> 16);
+      }
+    }
+  } else {
+    const unsigned w[4] = {g.v[0].x, g.v[0].y, g.v[0].z, g.v[0].w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      x[4 * k + 0] = fmt.unpack(w[k] & 0xFFu);
+      x[4 * k + 1] = fmt.unpack((w[k] >> 8) & 0xFFu);
+      x[4 * k + 2] = fmt.unpack((w[k] >> 16) & 0xFFu);
+      x[4 * k + 3] = fmt.unpack(w[k] >> 24);
+    }
+  }
+}
+template <int WIRE, class F>
+__device__ __forceinline__ Granule<WIRE> granule_encode(const F& fmt, const float (&x)[16]) {
+  Granule<WIRE> g;
+  if (WIRE == 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      g.v[i] = make_uint4(__float_as_uint(x[4 * i]), __float_as_uint(x[4 * i + 1]), __float_as_uint(x[4 * i + 2]),
+                          __float_as_uint(x[4 * i + 3]));
+  } else if (WIRE == 16) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      unsigned w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[k] = fmt.pack(x[8 * i + 2 * k]) | (fmt.pack(x[8 * i + 2 * k + 1]) << 16);
+      g.v[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+    unsigned w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      w[k] = fmt.pack(x[4 * k]) | (fmt.pack(x[4 * k + 1]) << 8) | (fmt.pack(x[4 * k + 2]) << 16) | (fmt.pack(x[4 * k + 3]) << 24);
+    g.v[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  return g;
+}
+
+__device__ __forceinline__ void load16(const float* p, float (&x)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(p + 4 * i);
+    x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void store16(float* p, const float (&x)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(p + 4 * i) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+}
+
+// ---- cross-GPU signalling -----------------------------------------------------
+// CTA 0 publishes `epoch` for `phase` into every peer's signal pad.
+__device__ __forceinline__ void signal_peers(const ArParams& p, int phase, unsigned epoch) {
+  if (blockIdx.x == 0 && threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(p.flags[threadIdx.x] + phase * kFlagStride + p.rank, epoch);
+  }
+}
+// every CTA waits until all peers have published `epoch` for `phase` (bounded spin).
+__device__ __forceinline__ void wait_peers(const ArParams& p, int phase, unsigned epoch) {
+  if (threadIdx.x < p.world) {
+    const unsigned* f = p.flags[p.rank] + phase * kFlagStride + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+      if ((unsigned long long)(clock64() - t0) > p.timeout) {
+        atomicExch(&p.ws[3], 0x80000000u | (unsigned(phase) << 8) | threadIdx.x);   // who is missing
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <class F, int WIRE, bool KAHAN>
+__global__ void __launch_bounds__(kArThreads)
+allreduce_fused_kernel(const ArParams p, const F fmt) {
+  __shared__ unsigned red[32];
+  __shared__ int s_shift[kArMaxT];
+  const int W = p.world, rank = p.rank;
+  const unsigned epoch = p.ws[2] + 1u;
+  const unsigned par = epoch & 1u;
+  unsigned* bar = p.ws;
+  unsigned* amax = p.ws + 4 + par * p.max_tensors;
+  unsigned char* my_data = p.data[rank] + par * p.cap_bytes;
+
+  // ---------------- phase A: per-tensor amax, exponent exchange ---------------------
+  if (p.use_aps) {
+    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
+      const Chunk ck = p.chunks[c];
+      unsigned m = 0u;
+      for (int g = threadIdx.x; g < (ck.len >> 4); g += kArThreads) {
+        const uint4* q = reinterpret_cast<const uint4*>(p.grad + ck.start + 16 * g);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 x = q[i];
+          m = max(max(m, x.x & 0x7FFFFFFFu), max(x.y & 0x7FFFFFFFu, max(x.z & 0x7FFFFFFFu, x.w & 0x7FFFFFFFu)));
+        }
+      }
+      m = block_max_u32(m, red);
+      if (threadIdx.x == 0 && m) atomicMax(&amax[ck.tensor], m);
+    }
+    grid_barrier(bar);
+    if (blockIdx.x == 0) {
+      float* mb = p.mailbox[rank] + par * p.max_tensors;
+      unsigned* amax_next = p.ws + 4 + (par ^ 1u) * p.max_tensors;
+      for (int t = threadIdx.x; t < p.T; t += kArThreads) {
+        const unsigned ab = amax[t];
+        mb[t] = ab >= 0x7F800000u ? INFINITY : aps_local_exponent(__uint_as_float(ab), (float)W);
+      }
+      // the other parity's amax buffer is used by the NEXT launch (possibly a different
+      // bucket with more tensors): clear all of it
+      for (int t = threadIdx.x; t < p.max_tensors; t += kArThreads) amax_next[t] = 0u;
+      __syncthreads();
+    }
+    signal_peers(p, 0, epoch);
+    wait_peers(p, 0, epoch);
+    for (int t = threadIdx.x; t < p.T; t += kArThreads) {
+      float me = -INFINITY;
+      for (int r = 0; r < W; ++r) {
+        const float v = ld_sys_f32(p.mailbox[r] + par * p.max_tensors + t);
+        me = (v != v || me != me) ? NAN : fmaxf(me, v);
+      }
+      const int sh = aps_shift_from_exponent(me, fmt.exp_bits());
+      s_shift[t] = sh;
+      if (p.shifts_out && blockIdx.x == 0) p.shifts_out[t] = sh;
+    }
+    __syncthreads();
+  }
+
+  // ---------------- phase B: scale, cast, pack into the local wire buffer -----------
+  for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
+    const Chunk ck = p.chunks[c];
+    const float sc = p.use_aps ? pow2i(s_shift[ck.tensor]) : 1.f;
+    for (int g = threadIdx.x; g < (ck.len >> 4); g += kArThreads) {
+      const long long e0 = ck.start + 16 * g;
+      float x[16];
+      load16(p.grad + e0, x);
+      if (p.use_aps) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = fmt.q(x[i] * sc);
+      } else if (p.prequant) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = fmt.q(x[i]);
+      }
+      granule_store<WIRE>(my_data, e0, granule_encode<WIRE>(fmt, x), false);
+    }
+  }
+  grid_barrier(bar);
+  signal_peers(p, 1, epoch);
+  wait_peers(p, 1, epoch);
+
+  // ---------------- phase C: rank-ordered quantised fold over peer memory ----------
+  const bool two_shot = p.algo != ALGO_ONESHOT;
+  const int c_begin = two_shot ? rank + W * (int)blockIdx.x : (int)blockIdx.x;
+  const int c_step = two_shot ? W * (int)gridDim.x : (int)gridDim.x;
+  for (int c = c_begin; c < p.n_chunks; c += c_step) {
+    const Chunk ck = p.chunks[c];
+    const float inv = p.use_aps ? pow2i(-s_shift[ck.tensor]) : 1.f;
+    for (int g = threadIdx.x; g < (ck.len >> 4); g += kArThreads) {
+      const long long e0 = ck.start + 16 * g;
+      // narrow wires: issue all W peer loads before the first use (W x 16..32 B in flight
+      // per thread hides the ~2 us NVLink latency); fp32 wire loads rank by rank.
+      constexpr int kPre = WIRE <= 16 ? kArMaxW : 1;
+      Granule<WIRE> in[kPre];
+      if (WIRE <= 16) {
+#pragma unroll
+        for (int r = 0; r < kPre; ++r)
+          if (r < W) in[r] = granule_load_sys<WIRE>(p.data[r] + par * p.cap_bytes, e0);
+      }
+      float s[16], cc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { s[i] = 0.f; cc[i] = 0.f; }
+#pragma unroll
+      for (int r = 0; r < kArMaxW; ++r) {
+        if (r < W) {
+          float v[16];
+          if (WIRE <= 16) granule_decode<WIRE>(fmt, in[r % kPre], v);
+          else granule_decode<WIRE>(fmt, granule_load_sys<WIRE>(p.data[r] + par * p.cap_bytes, e0), v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (KAHAN) fold_kahan(fmt, s[i], cc[i], v[i]);
+            else if (p.ident) s[i] += v[i];
+            else fold_plain(fmt, s[i], v[i]);
+          }
+        }
+      }
+      if (two_shot) {
+        const Granule<WIRE> out = granule_encode<WIRE>(fmt, s);
+        if (p.algo == ALGO_NVLS && p.mc_gather) {
+          granule_store_mc<WIRE>(p.mc_gather + par * p.cap_bytes, e0, out);
+        } else {
+#pragma unroll
+          for (int r = 0; r < kArMaxW; ++r)
+            if (r < W && r != rank) granule_store<WIRE>(p.gather[r] + par * p.cap_bytes, e0, out, true);
+        }
+      }
+      if (p.use_aps) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s[i] *= inv;
+      }
+      store16(p.grad + e0, s);
+    }
+  }
+
+  // ---------------- phase D (two-shot): adopt the slices reduced by the peers ---------
+  if (two_shot) {
+    grid_barrier(bar);
+    signal_peers(p, 2, epoch);
+    wait_peers(p, 2, epoch);
+    const unsigned char* my_gather = p.gather[rank] + par * p.cap_bytes;
+    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
+      if (c % W == rank) continue;
+      const Chunk ck = p.chunks[c];
+      const float inv = p.use_aps ? pow2i(-s_shift[ck.tensor]) : 1.f;
+      for (int g = threadIdx.x; g < (ck.len >> 4); g += kArThreads) {
+        const long long e0 = ck.start + 16 * g;
+        const Granule<WIRE> in = granule_load_sys<WIRE>(my_gather, e0);
+        float v[16];
+        granule_decode<WIRE>(fmt, in, v);
+        if (p.use_aps) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= inv;
+        }
+        store16(p.grad + e0, v);
+      }
+    }
+  }
+
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.ws[2] = epoch;
+}
+
+void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunks, int n_chunks, int T,
+                          int e, int m, bool use_aps, bool kahan, int algo, bool prequant, int wire,
+                          unsigned* local_ws, int* shifts_out, int max_ctas, unsigned long long timeout_cycles,
+                          cudaStream_t st) {
+  if (n_chunks <= 0) return;
+  ArParams p;
+  p.rank = cb.rank; p.world = cb.world;
+  for (int r = 0; r < kArMaxW; ++r) {
+    p.data[r] = r < cb.world ? cb.data[r] : nullptr;
+    p.gather[r] = r < cb.world ? cb.gather[r] : nullptr;
+    p.mailbox[r] = r < cb.world ? cb.mailbox[r] : nullptr;
+    p.flags[r] = r < cb.world ? cb.flags[r] : nullptr;
+  }
+  p.mc_gather = cb.mc_gather;
+  p.cap_bytes = (long long)cb.cap_bytes;
+  p.max_tensors = cb.max_tensors;
+  p.grad = grad; p.chunks = chunks; p.n_chunks = n_chunks; p.T = T;
+  p.use_aps = use_aps; p.algo = algo; p.prequant = prequant;
+  p.ident = (e == 8 && m == 23 && !kahan) ? 1 : 0;
+  p.ws = local_ws; p.shifts_out = shifts_out; p.timeout = timeout_cycles;
+  if (p.algo == ALGO_NVLS && !cb.mc_gather) p.algo = ALGO_TWOSHOT;
+  int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1);
+  if (grid > n_chunks) grid = n_chunks;
+
+#define CPD_AR_LAUNCH(WIRE_)                                                                          \
+  do {                                                                                                \
+    if (kahan) allreduce_fused_kernel<decltype(FMT), WIRE_, true><<<grid, kArThreads, 0, st>>>(p, FMT); \
+    else allreduce_fused_kernel<decltype(FMT), WIRE_, false><<<grid, kArThreads, 0, st>>>(p, FMT);      \
+  } while (0)
+
+  // compile-time formats carry their natural wire width; everything else goes through the
+  // runtime codec at the requested width
+  if (wire == 8 && e == 4 && m == 3) { FmtT<4, 3> FMT; CPD_AR_LAUNCH(8); }
+  else if (wire == 8 && e == 5 && m == 2) { FmtT<5, 2> FMT; CPD_AR_LAUNCH(8); }
+  else if (wire == 16 && e == 5 && m == 10) { FmtT<5, 10> FMT; CPD_AR_LAUNCH(16); }
+  else if (wire == 16 && e == 8 && m == 7) { FmtT<8, 7> FMT; CPD_AR_LAUNCH(16); }
+  else {
+    FmtR FMT{make_format(e, m, ROUND_REF)};
+    if (wire == 8) CPD_AR_LAUNCH(8);
+    else if (wire == 16) CPD_AR_LAUNCH(16);
+    else CPD_AR_LAUNCH(32);
+  }
+#undef CPD_AR_LAUNCH
+}
+
+}  // namespace cpd

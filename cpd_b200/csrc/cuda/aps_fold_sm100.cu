@@ -1,0 +1,112 @@
+// aps_fold_sm100.cu — single-GPU fused "APS + quantised ordered fold" over W local
+// gradient arenas, one launch for a whole bucket of tensors.
+//
+// Covers (a) emulate_node: W = E micro-batch gradient slots (reference
+// mix.py:251-285, main.py:178-202: per-parameter python loops with host syncs,
+// clone lists and ~10 launches per parameter per slot) and (b) the W == 1 case of
+// sum_gradients (dist_util.py:22-51 at world_size 1).  One persistent grid:
+//   phase A  per-tensor max|g| over all sources (uint-bit atomicMax per tensor)
+//   ---- grid barrier ----
+//   phase B  shift = bias - ceil(log2(amax * mult)); res = fold_r Q(g_r * 2^shift)
+//            (plain or Kahan, c in registers); out = res * 2^-shift
+// Chunks are 16-element aligned pieces of one tensor (arena padding is zero), so
+// every access is a 128-bit vector and one shift applies per chunk.
+#include "../api.h"
+#include "../common/fpformat.h"
+#include "../common/device_utils.cuh"
+#include "format_dispatch.cuh"
+
+namespace cpd {
+
+constexpr int kFoldThreads = 256;
+constexpr int kMaxLocalSrc = 16;
+
+struct SrcPtrs { const float* p[kMaxLocalSrc]; };
+
+template <class F, bool KAHAN>
+__global__ void __launch_bounds__(kFoldThreads)
+aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__ chunks,
+                      int n_chunks, int T, int T_cap, F fmt, bool use_aps, float world_mult,
+                      unsigned* __restrict__ ws, int* __restrict__ shifts_out) {
+  // ws layout: [0]=barrier count, [1]=barrier generation, [2]=launch counter, [4 .. 4+2*T_cap) = amax[2][T_cap]
+  __shared__ unsigned red[32];
+  unsigned* bar = ws;
+  const unsigned launch = ws[2];
+  unsigned* amax = ws + 4 + (launch & 1u) * T_cap;
+  unsigned* amax_next = ws + 4 + ((launch & 1u) ^ 1u) * T_cap;
+
+  if (use_aps) {
+    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+      const Chunk ck = chunks[c];
+      unsigned m = 0u;
+      for (int i = threadIdx.x * 4; i < ck.len; i += kFoldThreads * 4) {
+        for (int r = 0; r < W; ++r) {
+          const uint4 x = *reinterpret_cast<const uint4*>(srcs.p[r] + ck.start + i);
+          m = max(max(m, x.x & 0x7FFFFFFFu), max(x.y & 0x7FFFFFFFu, max(x.z & 0x7FFFFFFFu, x.w & 0x7FFFFFFFu)));
+        }
+      }
+      m = block_max_u32(m, red);
+      if (threadIdx.x == 0 && m) atomicMax(&amax[ck.tensor], m);
+    }
+    grid_barrier(bar);
+  }
+
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const Chunk ck = chunks[c];
+    int shift = 0;
+    if (use_aps) {
+      const unsigned ab = amax[ck.tensor];
+      const float me = ab >= 0x7F800000u ? INFINITY : aps_local_exponent(__uint_as_float(ab), world_mult);
+      shift = aps_shift_from_exponent(me, fmt.exp_bits());
+      if (shifts_out && threadIdx.x == 0) shifts_out[ck.tensor] = shift;
+    }
+    const float sc = pow2i(shift), inv = pow2i(-shift);
+    for (int i = threadIdx.x * 4; i < ck.len; i += kFoldThreads * 4) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f}, cc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int r = 0; r < W; ++r) {
+        const float4 g4 = *reinterpret_cast<const float4*>(srcs.p[r] + ck.start + i);
+        float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v = g[j];
+          if (use_aps) v = fmt.q(v * sc);
+          if (KAHAN) fold_kahan(fmt, s[j], cc[j], v);
+          else fold_plain(fmt, s[j], v);
+        }
+      }
+      float4 o;
+      if (use_aps) { o.x = s[0] * inv; o.y = s[1] * inv; o.z = s[2] * inv; o.w = s[3] * inv; }
+      else { o.x = s[0]; o.y = s[1]; o.z = s[2]; o.w = s[3]; }
+      *reinterpret_cast<float4*>(out + ck.start + i) = o;
+    }
+  }
+
+  // prepare the other amax buffer for the next launch and bump the launch counter.
+  // Safe without another barrier: nobody touches amax_next in this launch, and ws[2]
+  // was read by every CTA before the grid barrier (use_aps) or is only parity for amax.
+  if (use_aps && blockIdx.x == 0) {
+    for (int t = threadIdx.x; t < T_cap; t += kFoldThreads) amax_next[t] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) ws[2] = launch + 1u;
+  }
+}
+
+void aps_fold_local_cuda(const float* const* srcs_host, int W, float* out, const Chunk* chunks,
+                         int n_chunks, int T, int T_cap, int e, int m, bool use_aps, bool kahan, float world_mult,
+                         unsigned* workspace, int* shifts_out, int max_ctas, cudaStream_t st) {
+  if (n_chunks <= 0 || W <= 0) return;
+  SrcPtrs sp;
+  for (int r = 0; r < kMaxLocalSrc; ++r) sp.p[r] = r < W ? srcs_host[r] : nullptr;
+  int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1) * 2;
+  if (grid > n_chunks) grid = n_chunks;
+  CPD_DISPATCH_FORMAT(e, m, ROUND_REF, FMT, {
+    if (kahan)
+      aps_fold_local_kernel<decltype(FMT), true><<<grid, kFoldThreads, 0, st>>>(
+          sp, W, out, chunks, n_chunks, T, T_cap, FMT, use_aps, world_mult, workspace, shifts_out);
+    else
+      aps_fold_local_kernel<decltype(FMT), false><<<grid, kFoldThreads, 0, st>>>(
+          sp, W, out, chunks, n_chunks, T, T_cap, FMT, use_aps, world_mult, workspace, shifts_out);
+  });
+}
+
+}  // namespace cpd

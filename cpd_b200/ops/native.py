@@ -1,0 +1,246 @@
+"""Validated python entry points of the native ops (CPU C++ and sm_100a CUDA).
+
+Every function checks dtype / device / contiguity, picks the current CUDA stream of
+the tensor's device and forwards raw pointers to ``cpd_b200._C`` (which is torch-free).
+CUDA tensors always run the CUDA kernels; there is no eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .._ext import load
+
+_C = load()
+
+ROUND_REF = 0
+ROUND_IEEE = 1
+_ROUNDING = {"reference": ROUND_REF, "ref": ROUND_REF, "ieee": ROUND_IEEE, 0: 0, 1: 1}
+
+CHUNK_ELEMS = 4096          # elements per scheduling chunk (16 per thread x 256 threads)
+ALIGN_ELEMS = 16            # tensors start on 64-byte boundaries inside an arena
+CHUNK_DTYPE = np.dtype([("start", "<i8"), ("len", "<i4"), ("tensor", "<i4")])
+assert CHUNK_DTYPE.itemsize == _C.chunk_struct_size()
+
+ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS = 0, 1, 2, 3
+
+
+def rounding_code(rounding) -> int:
+    try:
+        return _ROUNDING[rounding]
+    except KeyError:
+        raise ValueError(f"rounding must be 'reference' or 'ieee', got {rounding!r}") from None
+
+
+def _check_fmt(exp: int, man: int) -> None:
+    if not (1 <= int(exp) <= 8):
+        raise ValueError(f"exp must be in [1, 8], got {exp}")
+    if not (0 <= int(man) <= 23):
+        raise ValueError(f"man must be in [0, 23], got {man}")
+
+
+def _f32(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} is not a torch.Tensor")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def wire_bits(exp: int, man: int) -> int:
+    return _C.wire_bits(int(exp), int(man))
+
+
+# ------------------------------------------------------------------ elementwise --
+def quantize_(inp: torch.Tensor, out: torch.Tensor, exp: int, man: int, rounding=ROUND_REF, shift: int = 0) -> torch.Tensor:
+    """out = Q_(exp,man)(inp * 2**shift); ``out`` may alias ``inp``.  Both contiguous fp32."""
+    _f32(inp, "input"); _f32(out, "out"); _check_fmt(exp, man)
+    if not (inp.is_contiguous() and out.is_contiguous()):
+        raise ValueError("quantize_: tensors must be contiguous")
+    if inp.numel() != out.numel() or inp.device != out.device:
+        raise ValueError("quantize_: input/out mismatch")
+    if not (-126 <= shift <= 127):
+        raise ValueError("shift out of range")
+    n = inp.numel()
+    if n == 0:
+        return out
+    r = rounding_code(rounding)
+    if inp.is_cuda:
+        with torch.cuda.device(inp.device):
+            _C.quantize_cuda(inp.data_ptr(), out.data_ptr(), n, int(exp), int(man), r, int(shift), _stream(inp))
+    else:
+        _C.quantize_cpu(inp.data_ptr(), out.data_ptr(), n, int(exp), int(man), r, int(shift))
+    return out
+
+
+def amax_bits(inp: torch.Tensor, out_u32: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """max |x| as fp32 bit pattern (int32 tensor of 1 element), CUDA only."""
+    _f32(inp, "input")
+    if not inp.is_cuda or not inp.is_contiguous():
+        raise ValueError("amax_bits: contiguous CUDA tensor expected")
+    if out_u32 is None:
+        out_u32 = torch.zeros(1, dtype=torch.int32, device=inp.device)
+    with torch.cuda.device(inp.device):
+        _C.amax_cuda(inp.data_ptr(), inp.numel(), out_u32.data_ptr(), _stream(inp))
+    return out_u32
+
+
+# ----------------------------------------------------------------------- GEMM --
+def gemm_exact(a: torch.Tensor, b: torch.Tensor, exp: int, man: int, rounding=ROUND_REF, kahan: bool = True,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = A @ B with the reference's per-MAC quantised (Kahan) sequential-k accumulation.
+    A and B may have arbitrary 2-D strides (transposed views are consumed in place)."""
+    _f32(a, "a"); _f32(b, "b"); _check_fmt(exp, man)
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[0]:
+        raise ValueError(f"gemm: bad shapes {tuple(a.shape)} x {tuple(b.shape)}")
+    if a.device != b.device:
+        raise ValueError("gemm: device mismatch")
+    M, K = a.shape
+    N = b.shape[1]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    else:
+        _f32(out, "out")
+        if tuple(out.shape) != (M, N) or not out.is_contiguous() or out.device != a.device:
+            raise ValueError("gemm: bad out tensor")
+    if M == 0 or N == 0:
+        return out
+    r = rounding_code(rounding)
+    args = (a.data_ptr(), a.stride(0), a.stride(1), b.data_ptr(), b.stride(0), b.stride(1), out.data_ptr(), out.stride(0),
+            M, N, K, int(exp), int(man), r, bool(kahan))
+    if a.is_cuda:
+        with torch.cuda.device(a.device):
+            _C.gemm_exact_cuda(*args, _stream(a))
+    else:
+        _C.gemm_exact_cpu(*args)
+    return out
+
+
+def gemm_tile_cpu(a, b, exp, man, rounding=ROUND_REF, kahan=False, k_slice=128, op_exp=8, op_man=23):
+    """CPU model of the tensor-core kernel's semantics (per-K-slice requantisation)."""
+    _f32(a, "a"); _f32(b, "b"); _check_fmt(exp, man)
+    M, K = a.shape
+    N = b.shape[1]
+    out = torch.empty(M, N, dtype=torch.float32)
+    _C.gemm_tile_cpu(a.data_ptr(), a.stride(0), a.stride(1), b.data_ptr(), b.stride(0), b.stride(1), out.data_ptr(),
+                     out.stride(0), M, N, K, int(exp), int(man), rounding_code(rounding), bool(kahan), int(k_slice),
+                     int(op_exp), int(op_man))
+    return out
+
+
+OPERAND_BF16, OPERAND_TF32, OPERAND_E4M3, OPERAND_E5M2 = 0, 1, 2, 3
+
+
+def gemm_tc(a: torch.Tensor, bt: torch.Tensor, exp: int, man: int, kahan: bool = False, k_slice: int = 128,
+            operand_mode: int = OPERAND_BF16, bias: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tcgen05 GEMM: C[M,N] = A[M,K] @ Bt[N,K]^T, accumulator re-quantised to (exp,man)
+    after every K-slice.  Operands must already be in the operand dtype (bf16 / fp32
+    for tf32 / float8)."""
+    _check_fmt(exp, man)
+    if not (a.is_cuda and bt.is_cuda and a.is_contiguous() and bt.is_contiguous()):
+        raise ValueError("gemm_tc: contiguous CUDA operands expected")
+    want = {OPERAND_BF16: torch.bfloat16, OPERAND_TF32: torch.float32, OPERAND_E4M3: torch.float8_e4m3fn,
+            OPERAND_E5M2: torch.float8_e5m2}[operand_mode]
+    if a.dtype != want or bt.dtype != want:
+        raise TypeError(f"gemm_tc: operand_mode {operand_mode} needs {want}, got {a.dtype}/{bt.dtype}")
+    M, K = a.shape
+    N = bt.shape[0]
+    if bt.shape[1] != K:
+        raise ValueError("gemm_tc: K mismatch")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _C.gemm_tc_cuda(a.data_ptr(), bt.data_ptr(), out.data_ptr(), M, N, K, int(exp), int(man), bool(kahan),
+                             int(k_slice), int(operand_mode), _ptr(bias), _stream(a))
+    if rc != 0:
+        raise RuntimeError(f"gemm_tc: kernel rejected the problem (code {rc})")
+    return out
+
+
+# --------------------------------------------------------- multi-tensor arenas --
+def aps_fold(srcs: Sequence[torch.Tensor], out: torch.Tensor, seg_off: torch.Tensor, exp: int, man: int,
+             use_aps: bool, kahan: bool, world_mult: float, chunks: Optional[torch.Tensor] = None,
+             workspace: Optional[torch.Tensor] = None, shifts_out: Optional[torch.Tensor] = None,
+             max_ctas: int = 0) -> torch.Tensor:
+    """APS + rank-ordered (Kahan) quantised fold over len(srcs) flat arenas -> out."""
+    _check_fmt(exp, man)
+    for s in srcs:
+        _f32(s, "src")
+        if not s.is_contiguous() or s.numel() != out.numel() or s.device != out.device:
+            raise ValueError("aps_fold: arenas must be flat, equal-sized and on one device")
+    _f32(out, "out")
+    T = seg_off.numel() - 1
+    if shifts_out is not None and (shifts_out.dtype != torch.int32 or shifts_out.numel() < T):
+        raise ValueError("shifts_out: int32[T] expected")
+    if out.is_cuda:
+        if chunks is None or workspace is None:
+            raise ValueError("aps_fold: CUDA path needs chunks and workspace")
+        if workspace.dtype != torch.int32 or workspace.numel() < 4 + 2 * T:
+            raise ValueError("aps_fold: workspace must be int32[4 + 2*T_cap] with T_cap >= T")
+        t_cap = (workspace.numel() - 4) // 2
+        n_chunks = chunks.numel() // CHUNK_DTYPE.itemsize
+        with torch.cuda.device(out.device):
+            _C.aps_fold_cuda([s.data_ptr() for s in srcs], out.data_ptr(), chunks.data_ptr(), n_chunks, T, t_cap, int(exp),
+                             int(man), bool(use_aps), bool(kahan), float(world_mult), workspace.data_ptr(),
+                             _ptr(shifts_out), int(max_ctas), _stream(out))
+    else:
+        if seg_off.dtype != torch.int64 or seg_off.is_cuda:
+            raise ValueError("seg_off: int64 CPU tensor expected")
+        _C.aps_fold_cpu([s.data_ptr() for s in srcs], out.data_ptr(), seg_off.data_ptr(), T, int(exp), int(man),
+                        bool(use_aps), bool(kahan), float(world_mult), _ptr(shifts_out))
+    return out
+
+
+def lars_step(master: torch.Tensor, model: Optional[torch.Tensor], grad: torch.Tensor, mom: torch.Tensor,
+              seg_off: torch.Tensor, lr: float, momentum: float, wd: float, coeff: float = 0.001, eps: float = 0.0,
+              use_lars: bool = True, nesterov: bool = False, wd_mult: Optional[torch.Tensor] = None,
+              chunks: Optional[torch.Tensor] = None, tchunk_off: Optional[torch.Tensor] = None,
+              lr_dev: Optional[torch.Tensor] = None, partials: Optional[torch.Tensor] = None,
+              barrier_ws: Optional[torch.Tensor] = None, max_ctas: int = 0) -> None:
+    for t, n in ((master, "master"), (grad, "grad"), (mom, "mom")):
+        _f32(t, n)
+        if not t.is_contiguous() or t.numel() != master.numel() or t.device != master.device:
+            raise ValueError("lars_step: arenas must be flat, equal-sized and on one device")
+    T = seg_off.numel() - 1
+    if master.is_cuda:
+        if chunks is None or tchunk_off is None or partials is None or barrier_ws is None:
+            raise ValueError("lars_step: CUDA path needs chunks, tchunk_off, partials, barrier_ws")
+        n_chunks = chunks.numel() // CHUNK_DTYPE.itemsize
+        if partials.numel() < 2 * n_chunks:
+            raise ValueError("lars_step: partials too small")
+        with torch.cuda.device(master.device):
+            _C.lars_step_cuda(master.data_ptr(), _ptr(model), grad.data_ptr(), mom.data_ptr(), chunks.data_ptr(),
+                              tchunk_off.data_ptr(), n_chunks, T, _ptr(lr_dev), float(lr), float(momentum), float(wd),
+                              float(coeff), float(eps), bool(use_lars), bool(nesterov), _ptr(wd_mult), partials.data_ptr(),
+                              barrier_ws.data_ptr(), int(max_ctas), _stream(master))
+    else:
+        lrv = float(lr_dev.item()) if lr_dev is not None else float(lr)
+        _C.lars_step_cpu(master.data_ptr(), _ptr(model), grad.data_ptr(), mom.data_ptr(), seg_off.data_ptr(), T, lrv,
+                         float(momentum), float(wd), float(coeff), float(eps), bool(use_lars), bool(nesterov), _ptr(wd_mult))
+
+
+def wire_roundtrip_cpu(x: torch.Tensor, exp: int, man: int) -> torch.Tensor:
+    _f32(x, "x")
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _C.wire_roundtrip_cpu(x.data_ptr(), out.data_ptr(), x.numel(), int(exp), int(man))
+    return out
+
+
+def topology() -> dict:
+    import json
+    return json.loads(_C.discover_topology_json())
+
+
+def sm_count(device: int = -1) -> int:
+    return _C.sm_count(device)

@@ -1,0 +1,219 @@
+"""Gradient reduction engine: the data-parallel low-precision all-reduce of CPD.
+
+Reference: ``sum_gradients`` (CPDtorch/utils/dist_util.py:22-89) — python loops over
+parameters, ~46 launches + 2 NCCL calls + host syncs per parameter, fp32 on the wire,
+no overlap.  ``GradReducer`` reduces a whole ``ModelArena`` in a handful of launches:
+
+  mode ``local``   world_size == 1: one fused APS-quantise kernel (aps_fold_sm100.cu)
+  mode ``fused``   world_size  > 1 on NVLink-connected GPUs: ONE sm_100a kernel per
+                   bucket that does amax exchange, scale, cast, pack, the rank-ordered
+                   (Kahan) fold over peer memory and the unscale
+                   (allreduce_fused_sm100a.cu; one-shot / two-shot / NVLS by size)
+  mode ``gather``  fallback + test oracle: the reference algorithm — all_gather of
+                   fp32 gradients (NCCL or Gloo) followed by one fold kernel over the
+                   W gathered copies.  Bit-identical to ``fused`` by construction.
+
+Buckets can be launched from autograd hooks on a dedicated comm stream so the
+reduction overlaps the rest of backward (``overlap=True``).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..config import PrecisionConfig
+from ..ops import native
+from .arena import ChunkTable, ModelArena
+
+_ALGO = {"auto": native.ALGO_AUTO, "oneshot": native.ALGO_ONESHOT, "twoshot": native.ALGO_TWOSHOT,
+         "nvls": native.ALGO_NVLS}
+
+# packed bytes per bucket below which the one-shot variant (1 exchange fewer, W x the
+# fold work and (W-1)/1 x the NVLink reads) beats two-shot; tuned on 8xB200
+ONESHOT_MAX_BYTES = 256 * 1024
+MAX_TENSORS_PER_BUCKET = 1024
+
+
+class GradReducer:
+    def __init__(self, arena: ModelArena, cfg: PrecisionConfig, group=None, mode: Optional[str] = None,
+                 timeout_cycles: int = 20_000_000_000):
+        self.arena = arena
+        self.cfg = cfg
+        self.group = group
+        self.device = arena.device
+        self.distributed = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if self.distributed else 1
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.timeout_cycles = int(timeout_cycles)
+        self.is_cuda = self.device.type == "cuda"
+
+        # wire width: narrow codes need already-quantised values (APS or prequantize)
+        nat = native.wire_bits(cfg.grad_exp, cfg.grad_man)
+        if cfg.wire != "auto":
+            self.wire = int(cfg.wire)
+            if self.wire < nat:
+                raise ValueError(f"wire={self.wire} cannot hold (exp={cfg.grad_exp}, man={cfg.grad_man}); need {nat}")
+        else:
+            self.wire = nat
+        if not (cfg.use_aps or cfg.prequantize):
+            self.wire = 32          # raw fp32 gradients travel: the first cast happens inside the fold
+
+        if mode is None:
+            if self.world == 1:
+                mode = "local"
+            elif cfg.algo == "nccl" or not self.is_cuda:
+                mode = "gather"
+            else:
+                mode = "fused"
+        self.mode = mode
+
+        ranges = arena.bucket_ranges(cfg.bucket_mb * (1 << 20))
+        split = []
+        for (a, b) in ranges:                      # the kernels keep per-tensor shifts in shared memory
+            while b - a > MAX_TENSORS_PER_BUCKET:
+                split.append((b - MAX_TENSORS_PER_BUCKET, b))
+                b -= MAX_TENSORS_PER_BUCKET
+            split.append((a, b))
+        self.buckets: List[ChunkTable] = [arena.table(a, b) for (a, b) in split]
+        self.max_T = max(b.T for b in self.buckets)
+        self.max_numel = max(b.numel for b in self.buckets)
+        self.shifts = [torch.zeros(b.T, dtype=torch.int32, device=self.device) for b in self.buckets]
+
+        self.local_ws = None
+        self.symm = None
+        self._gather_buf = None
+        if self.is_cuda:
+            self.local_ws = torch.zeros(4 + 2 * MAX_TENSORS_PER_BUCKET, dtype=torch.int32, device=self.device)
+        if self.mode == "fused":
+            from .symm import SymmetricWorkspace
+            self.symm = SymmetricWorkspace(self.max_numel * (self.wire // 8), MAX_TENSORS_PER_BUCKET, group=group)
+        elif self.mode == "gather" and self.world > 1:
+            self._gather_buf = torch.empty(self.world, self.max_numel, dtype=torch.float32, device=self.device)
+
+        # overlap machinery
+        self._hooks = []
+        self._pending = None
+        self._comm_stream = None
+        self._launched = []
+        if cfg.overlap and self.is_cuda and self.mode in ("fused", "gather", "local"):
+            self._install_hooks()
+
+    # ------------------------------------------------------------------ helpers --
+    def _bucket_view(self, flat: torch.Tensor, b: ChunkTable) -> torch.Tensor:
+        return flat[b.base:b.base + b.numel]
+
+    def algo_for(self, b: ChunkTable) -> int:
+        a = _ALGO.get(self.cfg.algo, native.ALGO_AUTO)
+        if a != native.ALGO_AUTO:
+            return a
+        nbytes = b.numel * (self.wire // 8)
+        if self.world <= 2 or nbytes <= ONESHOT_MAX_BYTES:
+            return native.ALGO_ONESHOT
+        return native.ALGO_NVLS if (self.symm is not None and self.symm.has_multicast) else native.ALGO_TWOSHOT
+
+    # ------------------------------------------------------------------- reduce --
+    def reduce_bucket(self, i: int, grad_flat: Optional[torch.Tensor] = None) -> None:
+        cfg, b = self.cfg, self.buckets[i]
+        g = self._bucket_view(self.arena.grad_flat if grad_flat is None else grad_flat, b)
+        e, m = cfg.grad_exp, cfg.grad_man
+        if self.mode == "local":
+            if cfg.is_fp32 and not cfg.use_kahan and not cfg.use_aps:
+                return                                           # fp32 all-reduce over one rank: nothing to do
+            native.aps_fold([g], g, b.seg_off, e, m, cfg.use_aps, cfg.use_kahan, 1.0, chunks=b.chunks,
+                            workspace=self.local_ws, shifts_out=self.shifts[i], max_ctas=cfg.comm_ctas)
+        elif self.mode == "fused":
+            native._C.allreduce_fused_cuda(
+                self.symm.buffers, g.data_ptr(), b.numel, b.chunks.data_ptr(), b.n_chunks, b.T, e, m,
+                bool(cfg.use_aps), bool(cfg.use_kahan), self.algo_for(b), bool(cfg.prequantize), self.wire,
+                self.local_ws.data_ptr(), self.shifts[i].data_ptr(), int(cfg.comm_ctas), self.timeout_cycles,
+                torch.cuda.current_stream(self.device).cuda_stream)
+        else:  # gather: the reference algorithm, one collective + one fold launch per bucket
+            if cfg.is_fp32 and not cfg.use_kahan and not cfg.use_aps:
+                dist.all_reduce(g, group=self.group)             # dist_util.py:55-59
+                return
+            buf = self._gather_buf[:, :b.numel]
+            dist.all_gather([buf[r] for r in range(self.world)], g, group=self.group)
+            srcs = [buf[r] for r in range(self.world)]
+            if cfg.prequantize and not cfg.use_aps:
+                for s in srcs:
+                    native.quantize_(s, s, e, m)
+            native.aps_fold(srcs, g, b.seg_off, e, m, cfg.use_aps, cfg.use_kahan, float(self.world), chunks=b.chunks,
+                            workspace=self.local_ws, shifts_out=self.shifts[i], max_ctas=cfg.comm_ctas)
+
+    def reduce(self, grad_flat: Optional[torch.Tensor] = None) -> None:
+        """Reduce every bucket now (call after backward)."""
+        if self._pending is not None:
+            self.finish()
+            return
+        for i in range(len(self.buckets)):
+            self.reduce_bucket(i, grad_flat)
+
+    # ------------------------------------------------------------------ overlap --
+    def _install_hooks(self) -> None:
+        self._comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        owner = {}
+        for bi, b in enumerate(self.buckets):
+            for t in range(b.t0, b.t1):
+                owner[t] = bi
+        self._bucket_need = [b.T for b in self.buckets]
+        self._pending = [0] * len(self.buckets)
+        self._armed = False
+
+        def make_hook(bi):
+            def hook(_param):
+                if not self._armed:
+                    return
+                self._pending[bi] += 1
+                if self._pending[bi] == self._bucket_need[bi]:
+                    self._launch_async(bi)
+            return hook
+
+        for t, p in enumerate(self.arena.params):
+            self._hooks.append(p.register_post_accumulate_grad_hook(make_hook(owner[t])))
+
+    def arm(self) -> None:
+        """Call before backward when overlap is on: buckets launch as soon as they fill."""
+        if self._pending is not None:
+            self._pending = [0] * len(self.buckets)
+            self._launched = []
+            self._armed = True
+
+    def _launch_async(self, bi: int) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._comm_stream.wait_event(ev)
+        with torch.cuda.stream(self._comm_stream):
+            self.reduce_bucket(bi)
+        self._launched.append(bi)
+
+    def finish(self) -> None:
+        """Join the comm stream; reduce any bucket whose hooks did not all fire (e.g. unused params)."""
+        if self._pending is None:
+            return
+        self._armed = False
+        for bi in range(len(self.buckets)):
+            if bi not in self._launched:
+                self._launch_async(bi)
+        done = torch.cuda.Event()
+        done.record(self._comm_stream)
+        torch.cuda.current_stream(self.device).wait_event(done)
+        self._launched = []
+
+    # ------------------------------------------------------------------- status --
+    def check_status(self) -> None:
+        """Raise if a fused kernel timed out waiting for a peer (host-side sync point)."""
+        if self.local_ws is None:
+            return
+        st = int(self.local_ws[3].item()) & 0xFFFFFFFF
+        if st & 0x80000000:
+            phase, peer = (st >> 8) & 0xFF, st & 0xFF
+            raise RuntimeError(f"cpd_b200: fused all-reduce timed out in phase {phase} waiting for rank {peer}")
+
+    def remove_hooks(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        self._pending = None

@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    config.addinivalue_line("markers", "multigpu: needs >= 2 CUDA devices")
+    config.addinivalue_line("markers", "slow: long-running")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_cuda = torch.cuda.is_available()
+        ngpu = torch.cuda.device_count() if has_cuda else 0
+    except Exception:  # pragma: no cover
+        has_cuda, ngpu = False, 0
+    skip_gpu = pytest.mark.skip(reason="no CUDA device")
+    skip_multi = pytest.mark.skip(reason="needs >= 2 CUDA devices")
+    for item in items:
+        if "gpu" in item.keywords and not has_cuda:
+            item.add_marker(skip_gpu)
+        if "multigpu" in item.keywords and ngpu < 2:
+            item.add_marker(skip_multi)
