@@ -1,0 +1,16 @@
+from .resnet_cifar import resnet18_cifar, resnet34_cifar, ResNetCifar  # noqa: F401
+from .resnet_imagenet import resnet18, resnet34, resnet50, resnet101, ResNet  # noqa: F401
+from .davidnet import davidnet, GraphNet  # noqa: F401
+
+_REGISTRY = {
+    "resnet18_cifar": resnet18_cifar, "res_cifar": resnet18_cifar, "resnet34_cifar": resnet34_cifar,
+    "resnet18": resnet18, "resnet34": resnet34, "resnet50": resnet50, "resnet101": resnet101,
+    "davidnet": davidnet,
+}
+
+
+def create_model(name: str, **kw):
+    try:
+        return _REGISTRY[name](**kw)
+    except KeyError:
+        raise ValueError(f"unknown model {name!r}; available: {sorted(_REGISTRY)}") from None

@@ -1,0 +1,181 @@
+"""Training engine: one call per optimizer step, everything on-device.
+
+Replaces the reference trainers' inner loops (example/ResNet18/tools/mix.py:201-358,
+example/ResNet50/main.py:141-212, example/DavidNet/utils.py:328-378) — python loops over
+parameters with host syncs between hundreds of tiny kernels — by a fixed device-side
+pipeline that is captured ONCE into a CUDA graph and replayed:
+
+    H2D(inputs, pinned)  ->  [ E x (zero slot, forward, loss/(W*E), backward) ]
+                         ->  emulate_node fold   (1 kernel, aps_fold_sm100.cu)
+                         ->  gradient all-reduce (1 fused kernel per bucket, allreduce_fused_sm100a.cu)
+                         ->  LARS / SGD on fp32 masters + master->model copy (1 kernel, lars_sm100.cu)
+                         ->  D2H(loss)
+
+Gradients, parameters, masters and momentum live in flat arenas (parallel/arena.py), the
+learning rate is read from device memory, and the cross-GPU kernels keep their epochs on
+the device, so graph replay needs no host-side bookkeeping.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..config import PrecisionConfig
+from ..optim import FusedSGD
+from ..parallel.api import broadcast_params
+from ..parallel.arena import ModelArena
+from ..parallel.emulate import EmulateNode
+from ..parallel.reducer import GradReducer
+
+
+class TrainEngine:
+    def __init__(self, model: nn.Module, cfg: PrecisionConfig, *, batch_size: int, input_shape: Sequence[int] = (3, 32, 32),
+                 lr: float = 0.1, momentum: float = 0.9, weight_decay: float = 1e-4, use_lars: bool = False,
+                 nesterov: bool = False, wd_mult: Optional[Sequence[float]] = None, loss_reduction: str = "mean",
+                 loss_scale: float = 1.0, channels_last: bool = True, cuda_graph: bool = True,
+                 fold_single: bool = False, device: Optional[torch.device] = None, master_weights: bool = True,
+                 lars_eps: float = 0.0, warmup_steps: int = 3):
+        self.cfg = cfg
+        self.distributed = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size() if self.distributed else 1
+        self.rank = dist.get_rank() if self.distributed else 0
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self.device = device
+        self.is_cuda = device.type == "cuda"
+        self.E = int(cfg.emulate_node)
+        self.batch_size = int(batch_size)
+        self.loss_reduction, self.loss_scale = loss_reduction, float(loss_scale)
+
+        model = model.to(device)
+        self.channels_last = bool(channels_last and self.is_cuda)
+        if self.channels_last:
+            model = model.to(memory_format=torch.channels_last)
+        self.model = model
+        broadcast_params(model)                                   # DistModule semantics: rank 0's init everywhere
+        self.arena = ModelArena(list(model.parameters()))
+        model._cpd_arena = self.arena
+        self.emulate = EmulateNode(self.arena, cfg, fold_single=fold_single)
+        self.reducer = GradReducer(self.arena, cfg)
+        self.optimizer = FusedSGD(self.arena, lr=lr, momentum=momentum, weight_decay=weight_decay, use_lars=use_lars,
+                                  nesterov=nesterov, wd_mult=wd_mult, master_weights=master_weights, lars_eps=lars_eps)
+
+        self.x = torch.zeros(self.E, self.batch_size, *input_shape, device=device)
+        self.y = torch.zeros(self.E, self.batch_size, dtype=torch.long, device=device)
+        self.loss_dev = torch.zeros(1, device=device)
+        self.loss_host = torch.zeros(1).pin_memory() if self.is_cuda else torch.zeros(1)
+        self.step_count = 0
+        self.graph = None
+        self._use_graph = bool(cuda_graph and self.is_cuda)
+        self._warmup_left = int(warmup_steps) if self._use_graph else 0
+        self._done_evt = torch.cuda.Event() if self.is_cuda else None
+        self.kernel_launches_per_step = None
+
+    # ------------------------------------------------------------------ step body --
+    def _loss(self, logits, target):
+        red = "sum" if self.loss_reduction == "sum" else "mean"
+        return F.cross_entropy(logits, target, reduction=red)
+
+    def _step_body(self) -> None:
+        self.loss_dev.zero_()
+        denom = float(self.world * self.E)
+        overlap = self.cfg.overlap and self.E == 1
+        for k in range(self.E):
+            self.emulate.begin_micro(k)
+            xin = self.x[k]
+            if self.channels_last:
+                xin = xin.contiguous(memory_format=torch.channels_last)
+            out = self.model(xin)
+            loss = self._loss(out, self.y[k]) / denom
+            if overlap:
+                self.reducer.arm()
+            (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
+            self.loss_dev += loss.detach()
+        self.emulate.fold()
+        self.reducer.reduce()
+        self.optimizer.step()
+
+    def _capture(self) -> None:
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step_body()
+
+    # ------------------------------------------------------------------- public --
+    def set_lr(self, lr: float) -> None:
+        self.optimizer.set_lr(lr)
+
+    def load_batch(self, images: torch.Tensor, labels: torch.Tensor) -> None:
+        """Host -> device copy of one step's inputs ([E*B, ...] or [E, B, ...]); pinned sources are async."""
+        self.x.view(-1, *self.x.shape[2:]).copy_(images.view(-1, *self.x.shape[2:]), non_blocking=True)
+        self.y.view(-1).copy_(labels.view(-1), non_blocking=True)
+
+    def run_step(self) -> None:
+        """One optimizer step on the inputs already in the static buffers (no host sync)."""
+        if self._use_graph:
+            if self._warmup_left > 0:
+                s = torch.cuda.Stream(device=self.device)
+                s.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(s):
+                    self._step_body()
+                torch.cuda.current_stream(self.device).wait_stream(s)
+                self._warmup_left -= 1
+            else:
+                if self.graph is None:
+                    self._capture()
+                self.graph.replay()
+        else:
+            self._step_body()
+        self.step_count += 1
+
+    def train_step(self, images: torch.Tensor, labels: torch.Tensor, lr: Optional[float] = None) -> float:
+        """The call a user makes: H2D the batch, one full step, D2H the (local, already /W) loss."""
+        if lr is not None:
+            self.set_lr(lr)
+        self.load_batch(images, labels)
+        self.run_step()
+        if self.is_cuda:
+            self.loss_host.copy_(self.loss_dev, non_blocking=True)
+            self._done_evt.record()
+            self._done_evt.synchronize()
+        else:
+            self.loss_host.copy_(self.loss_dev)
+        return float(self.loss_host[0])
+
+    @torch.no_grad()
+    def evaluate(self, images: torch.Tensor, labels: torch.Tensor):
+        was = self.model.training
+        self.model.eval()
+        x = images.to(self.device, non_blocking=True)
+        if self.channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
+        out = self.model(x)
+        y = labels.to(self.device, non_blocking=True)
+        loss = F.cross_entropy(out, y)
+        self.model.train(was)
+        return out, loss
+
+    def global_loss(self) -> float:
+        """Sum of the per-rank (already divided by W*E) losses = the global mean loss (logging)."""
+        t = self.loss_dev.clone()
+        if self.world > 1:
+            dist.all_reduce(t)
+        return float(t.item())
+
+    def check(self) -> None:
+        self.reducer.check_status()
+
+    def state_dict(self) -> dict:
+        return {"model": {k: v.detach().cpu() for k, v in self.model.state_dict().items()},
+                "optimizer": self.optimizer.state_dict(), "step": self.step_count, "precision": self.cfg.to_dict()}
+
+    def load_state_dict(self, sd: dict) -> None:
+        with torch.no_grad():
+            cur = self.model.state_dict()
+            for k, v in sd["model"].items():
+                cur[k].copy_(v)
+        self.optimizer.load_state_dict(sd["optimizer"])
+        self.step_count = int(sd.get("step", 0))

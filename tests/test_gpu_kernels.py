@@ -1,0 +1,160 @@
+"""CUDA kernels == C++ CPU ops bit for bit (SURVEY §4 'Unit, GPU'); run on the B200 via gpurun."""
+import numpy as np
+import pytest
+import torch
+
+from cpd_b200 import float_quantize, quant_gemm, PrecisionConfig
+from cpd_b200.ops import native
+from cpd_b200.parallel.arena import ArenaLayout
+
+pytestmark = pytest.mark.gpu
+FORMATS = [(4, 3), (5, 2), (3, 0), (5, 10), (8, 7), (8, 23), (6, 9), (2, 1)]
+
+
+def _bits(n, seed):
+    rng = np.random.default_rng(seed)
+    return torch.from_numpy(rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32).view(np.float32).copy())
+
+
+def _same(a, b):
+    a, b = a.cpu(), b.cpu()
+    return bool(((a.view(torch.int32) == b.view(torch.int32)) | (a.isnan() & b.isnan())).all())
+
+
+@pytest.mark.parametrize("e,m", FORMATS)
+@pytest.mark.parametrize("rounding", ["reference", "ieee"])
+def test_quantize_matches_cpu(e, m, rounding):
+    x = _bits((1 << 20) + 3, e * 31 + m)
+    got = float_quantize(x.cuda(), e, m, rounding=rounding)
+    assert _same(got, float_quantize(x, e, m, rounding=rounding))
+
+
+def test_quantize_variants():
+    x = torch.randn(100003) * 1e-2
+    xc = x.cuda()
+    assert _same(float_quantize(xc, 4, 3, shift=9), float_quantize(x, 4, 3, shift=9))
+    y = xc.clone()
+    r = float_quantize(y, 5, 2, inplace=True)
+    assert r.data_ptr() == y.data_ptr() and _same(r, float_quantize(x, 5, 2))
+    assert _same(float_quantize(xc[1:], 4, 3), float_quantize(x[1:], 4, 3))           # unaligned base pointer
+    assert _same(float_quantize(xc.view(-1)[::2], 4, 3), float_quantize(x[::2], 4, 3))  # non-contiguous
+    assert float_quantize(torch.empty(0, device="cuda"), 4, 3).numel() == 0
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        z = float_quantize(xc, 4, 3)
+    s.synchronize()
+    assert _same(z, float_quantize(x, 4, 3))
+    ab = native.amax_bits(xc)
+    assert ab.view(torch.float32).item() == x.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (1, 1, 1), (17, 65, 33), (130, 70, 257), (10, 512, 48)])
+@pytest.mark.parametrize("e,m,kahan", [(4, 3, True), (5, 2, True), (5, 10, False), (8, 23, True)])
+def test_gemm_exact_matches_cpu(M, N, K, e, m, kahan):
+    torch.manual_seed(M + N + K)
+    a, b = torch.randn(M, K), torch.randn(K, N)
+    got = native.gemm_exact(a.cuda(), b.cuda(), e, m, kahan=kahan)
+    assert _same(got, native.gemm_exact(a, b, e, m, kahan=kahan))
+    gt = native.gemm_exact(a.t().contiguous().cuda().t(), b.t().contiguous().cuda().t(), e, m, kahan=kahan)
+    assert _same(gt, got)
+
+
+def _arenas(W, numels, seed, device):
+    rng = np.random.default_rng(seed)
+    layout = ArenaLayout(numels)
+    out = []
+    for r in range(W):
+        flat = torch.zeros(layout.total)
+        for t, n in enumerate(numels):
+            flat[layout.offsets[t]:layout.offsets[t] + n] = torch.from_numpy(
+                (rng.standard_normal(n) * 2.0 ** rng.integers(-18, 3)).astype(np.float32))
+        out.append(flat)
+    return layout, out
+
+
+@pytest.mark.parametrize("W", [1, 2, 8])
+@pytest.mark.parametrize("e,m", [(4, 3), (5, 2), (5, 10), (6, 9)])
+@pytest.mark.parametrize("aps,kahan", [(True, False), (True, True), (False, False), (False, True)])
+def test_aps_fold_matches_cpu(W, e, m, aps, kahan):
+    numels = [10, 64, 1, 4097, 300, 70000, 0 + 5]
+    layout, cpu = _arenas(W, numels, W * 7 + e, "cpu")
+    tab_c, tab_g = layout.table("cpu"), layout.table("cuda")
+    want = torch.empty(layout.total)
+    sh_c = torch.zeros(len(numels), dtype=torch.int32)
+    native.aps_fold(cpu, want, tab_c.seg_off, e, m, aps, kahan, float(W), shifts_out=sh_c)
+    gpu = [a.cuda() for a in cpu]
+    got = torch.empty(layout.total, device="cuda")
+    ws = torch.zeros(4 + 2 * 64, dtype=torch.int32, device="cuda")
+    sh_g = torch.zeros(len(numels), dtype=torch.int32, device="cuda")
+    for rep in range(3):          # repeated launches exercise the double-buffered amax workspace
+        native.aps_fold(gpu, got, tab_g.seg_off, e, m, aps, kahan, float(W), chunks=tab_g.chunks, workspace=ws, shifts_out=sh_g)
+        assert _same(got, want), (rep, W, e, m, aps, kahan)
+        if aps:
+            assert torch.equal(sh_g.cpu(), sh_c)
+    # in place (W == 1 path of sum_gradients)
+    if W == 1:
+        g0 = gpu[0].clone()
+        native.aps_fold([g0], g0, tab_g.seg_off, e, m, aps, kahan, 1.0, chunks=tab_g.chunks, workspace=ws)
+        assert _same(g0, want)
+
+
+@pytest.mark.parametrize("use_lars,nesterov", [(True, False), (False, False), (False, True)])
+def test_lars_matches_cpu(use_lars, nesterov):
+    numels = [64, 3000, 10, 50000, 4096]
+    layout = ArenaLayout(numels)
+    torch.manual_seed(0)
+    master = torch.zeros(layout.total)
+    grad = torch.zeros(layout.total)
+    for t, n in enumerate(numels):
+        master[layout.offsets[t]:layout.offsets[t] + n] = torch.randn(n)
+        grad[layout.offsets[t]:layout.offsets[t] + n] = torch.randn(n) * 0.01
+    mom = torch.zeros(layout.total)
+    wdm = torch.tensor([1.0, 0.0, 1.0, 1.0, 0.5])
+    tc, tg = layout.table("cpu"), layout.table("cuda")
+    mg, gg, bg, modelg = master.cuda(), grad.cuda(), mom.cuda(), torch.zeros(layout.total, device="cuda")
+    lr_dev = torch.tensor([0.1], device="cuda")
+    partials = torch.zeros(2 * tg.n_chunks, device="cuda")
+    bar = torch.zeros(4, dtype=torch.int32, device="cuda")
+    for step in range(3):
+        native.lars_step(master, None, grad, mom, tc.seg_off, lr=0.1, momentum=0.9, wd=1e-4, use_lars=use_lars, nesterov=nesterov, wd_mult=wdm)
+        native.lars_step(mg, modelg, gg, bg, tg.seg_off, lr=0.0, momentum=0.9, wd=1e-4, use_lars=use_lars, nesterov=nesterov,
+                         wd_mult=wdm.cuda(), chunks=tg.chunks, tchunk_off=tg.tchunk_off, lr_dev=lr_dev, partials=partials, barrier_ws=bar)
+    assert torch.allclose(mg.cpu(), master, rtol=2e-5, atol=1e-7)
+    assert torch.allclose(bg.cpu(), mom, rtol=2e-5, atol=1e-7)
+    assert torch.equal(modelg, mg)
+
+
+def test_engine_graph_matches_eager_and_learns():
+    from cpd_b200.models import create_model
+    from cpd_b200.train import TrainEngine
+    xb = torch.randn(64, 3, 32, 32).pin_memory()
+    yb = torch.randint(0, 10, (64,)).pin_memory()
+    runs = []
+    for graph in (False, True):
+        torch.manual_seed(0)
+        eng = TrainEngine(create_model("davidnet"), PrecisionConfig(grad_exp=5, grad_man=2, use_aps=True, use_kahan=True),
+                          batch_size=64, lr=0.02, weight_decay=5e-4, use_lars=False, nesterov=True, cuda_graph=graph, warmup_steps=2)
+        torch.backends.cudnn.deterministic = True
+        runs.append([eng.train_step(xb, yb) for _ in range(6)])
+    assert runs[0][-1] < runs[0][0]
+    assert np.allclose(runs[0], runs[1], rtol=2e-2), runs
+
+
+def test_engine_emulate_node_equals_cpu_semantics():
+    """emulate_node=4 on the GPU == the C++ CPU op on the same micro-gradients (bitwise)."""
+    from cpd_b200.parallel import ModelArena, EmulateNode
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(33, 17), torch.nn.ReLU(), torch.nn.Linear(17, 5)).cuda()
+    arena = ModelArena(list(lin.parameters()))
+    cfg = PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, emulate_node=4)
+    em = EmulateNode(arena, cfg)
+    xs = [torch.randn(8, 33, device="cuda") for _ in range(4)]
+    for k in range(4):
+        em.begin_micro(k)
+        (lin(xs[k]).square().mean() / 4).backward()
+    slots_cpu = [s.cpu() for s in em.slots]
+    em.fold()
+    want = torch.empty(arena.layout.total)
+    native.aps_fold(slots_cpu, want, arena.layout.table("cpu").seg_off, 4, 3, True, False, 4.0)
+    assert _same(arena.grad_flat, want)
+    assert lin[0].weight.grad.data_ptr() == arena.grad_views[0].data_ptr()

@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Single-GPU micro-benchmarks of the elementwise / multi-tensor kernels with roofline fractions
+(measured HBM copy bandwidth from MEASURED_PEAKS.json).  CUDA-event timed, L2 flushed between
+iterations by writing a 256 MiB buffer.  Prints one JSON object."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cpd_b200 import float_quantize, quant_gemm  # noqa: E402
+from cpd_b200.ops import native  # noqa: E402
+from cpd_b200.parallel.arena import ArenaLayout  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+_flush = None
+
+
+def time_ms(fn, iters=10, warm=3, flush=True):
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            _flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    hbm, tflops, src = peaks()
+    res = {"peaks": {"hbm_gbs": hbm, "bf16_tflops": tflops, "source": src}, "quantize": [], "aps_fold": [], "lars": [], "gemm_exact": []}
+    sizes = [1 << 24] if args.quick else [1 << 20, 1 << 24, 1 << 28]
+    for n in sizes:
+        x = torch.randn(n, device="cuda")
+        out = torch.empty_like(x)
+        for (e, m) in [(4, 3), (5, 2)] if not args.quick else [(4, 3)]:
+            ms = time_ms(lambda: native.quantize_(x, out, e, m))
+            gbs = 8 * n / ms / 1e6
+            res["quantize"].append({"n": n, "fmt": [e, m], "ms": round(ms, 4), "GBps": round(gbs, 1), "frac_of_hbm_" + src: round(gbs / hbm, 3)})
+        del x, out
+    # whole-model fused kernels on the ResNet-18 layout (62 tensors, 11.17 M elements)
+    from cpd_b200.models import create_model
+    numels = [p.numel() for p in create_model("resnet18_cifar").parameters()]
+    layout = ArenaLayout(numels)
+    tab = layout.table("cuda")
+    ws = torch.zeros(4 + 2 * 128, dtype=torch.int32, device="cuda")
+    for W in ([1] if args.quick else [1, 8]):
+        srcs = [torch.randn(layout.total, device="cuda") * 1e-3 for _ in range(W)]
+        out = torch.empty(layout.total, device="cuda")
+        for kahan in (False, True):
+            ms = time_ms(lambda: native.aps_fold(srcs, out, tab.seg_off, 4, 3, True, kahan, float(W), chunks=tab.chunks, workspace=ws))
+            byts = layout.total * 4 * (W + 1)          # algorithmic: read W arenas once (2nd pass hits L2), write one
+            res["aps_fold"].append({"W": W, "kahan": kahan, "elems": layout.total, "ms": round(ms, 4), "GBps_algorithmic": round(byts / ms / 1e6, 1),
+                                    "frac_of_hbm_" + src: round(byts / ms / 1e6 / hbm, 3)})
+    master, grad, mom, model = (torch.randn(layout.total, device="cuda") for _ in range(4))
+    partials = torch.zeros(2 * tab.n_chunks, device="cuda")
+    bar = torch.zeros(4, dtype=torch.int32, device="cuda")
+    lr_dev = torch.tensor([0.1], device="cuda")
+    for use_lars in (True, False):
+        ms = time_ms(lambda: native.lars_step(master, model, grad, mom, tab.seg_off, 0.1, 0.9, 1e-4, use_lars=use_lars, chunks=tab.chunks,
+                                              tchunk_off=tab.tchunk_off, lr_dev=lr_dev, partials=partials, barrier_ws=bar))
+        byts = layout.total * 4 * 6                     # read w,g,m ; write w,m,model
+        res["lars"].append({"use_lars": use_lars, "ms": round(ms, 4), "GBps_algorithmic": round(byts / ms / 1e6, 1),
+                            "frac_of_hbm_" + src: round(byts / ms / 1e6 / hbm, 3)})
+    if not args.quick:
+        for n in (64, 1024):
+            a, b = torch.randn(n, n, device="cuda"), torch.randn(n, n, device="cuda")
+            ms = time_ms(lambda: quant_gemm(a, b, man=3, exp=4, mode="exact"), iters=5, flush=False)
+            res["gemm_exact"].append({"n": n, "ms": round(ms, 4), "GFLOPs": round(2 * n ** 3 / ms / 1e6, 1)})
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()
