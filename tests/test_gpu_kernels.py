@@ -158,3 +158,61 @@ def test_engine_emulate_node_equals_cpu_semantics():
     native.aps_fold(slots_cpu, want, arena.layout.table("cpu").seg_off, 4, 3, True, False, 4.0)
     assert _same(arena.grad_flat, want)
     assert lin[0].weight.grad.data_ptr() == arena.grad_views[0].data_ptr()
+
+
+# ---- tcgen05 tensor-core GEMM -----------------------------------------------------------
+def _tc_ref(a_op, bt_op, e, m, kahan, k_slice):
+    """CPU model of the tile semantics on the (already operand-rounded) inputs."""
+    return native.gemm_tile_cpu(a_op.float().cpu(), bt_op.float().cpu().t(), e, m, kahan=kahan, k_slice=k_slice)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 512), (200, 136, 264), (1, 8, 16), (1024, 64, 2304)])
+def test_gemm_tc_bf16_fp32_accumulator(M, N, K):
+    torch.manual_seed(M + K)
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    bt = torch.randn(N, K, device="cuda").bfloat16()
+    got = native.gemm_tc(a, bt, 8, 23, kahan=False, k_slice=0, operand_mode=native.OPERAND_BF16)
+    ref = a.float() @ bt.float().t()
+    assert (got - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-3, float((got - ref).abs().max())
+
+
+@pytest.mark.parametrize("mode,dt,tol", [(native.OPERAND_TF32, torch.float32, 2e-3), (native.OPERAND_E4M3, torch.float8_e4m3fn, 1e-4),
+                                          (native.OPERAND_E5M2, torch.float8_e5m2, 1e-4)])
+def test_gemm_tc_operand_kinds(mode, dt, tol):
+    torch.manual_seed(0)
+    a = (torch.randn(256, 256, device="cuda")).to(dt)
+    bt = (torch.randn(128, 256, device="cuda")).to(dt)
+    got = native.gemm_tc(a, bt, 8, 23, kahan=False, k_slice=0, operand_mode=mode)
+    ref = a.float() @ bt.float().t()
+    assert (got - ref).abs().max() <= tol * ref.abs().max() + 1e-3, float((got - ref).abs().max())
+
+
+@pytest.mark.parametrize("e,m,kahan,k_slice", [(5, 10, False, 128), (5, 10, True, 64), (4, 3, False, 128), (5, 2, True, 256), (8, 7, False, 64)])
+def test_gemm_tc_requant_matches_cpu_tile_model(e, m, kahan, k_slice):
+    torch.manual_seed(e * 10 + m)
+    M, N, K = 256, 256, 1024
+    a = (torch.randn(M, K, device="cuda") * 0.25).bfloat16()
+    bt = (torch.randn(N, K, device="cuda") * 0.25).bfloat16()
+    got = native.gemm_tc(a, bt, e, m, kahan=kahan, k_slice=k_slice, operand_mode=native.OPERAND_BF16).cpu()
+    want = _tc_ref(a, bt, e, m, kahan, k_slice)
+    # per-slice partials differ from the model only by fp32-vs-fp64 accumulation order, which can
+    # flip a rounding decision by one quantum of the format; require near-total agreement
+    quantum = 2.0 ** (-m)
+    rel = (got - want).abs() / want.abs().clamp_min(1e-6)
+    assert float((rel <= 2 * quantum).float().mean()) > 0.999
+    assert float((got == want).float().mean()) > 0.9
+
+
+def test_quant_gemm_tile_mode_and_linear_tile():
+    from cpd_b200 import Quant_Linear
+    torch.manual_seed(0)
+    a, b = torch.randn(512, 1024, device="cuda"), torch.randn(1024, 256, device="cuda")
+    ref = a @ b
+    for (e, m, tol) in [(5, 10, 2e-2), (8, 23, 5e-3)]:
+        c = quant_gemm(a, b, man=m, exp=e, mode="tile", k_slice=256)
+        assert (c - ref).abs().max() / ref.abs().max() < tol
+    lin = Quant_Linear(1024, 256, exp=5, man=10, mode="tile").cuda()
+    x = torch.randn(512, 1024, device="cuda", requires_grad=True)
+    y = lin(x)
+    y.sum().backward()
+    assert torch.isfinite(y).all() and torch.isfinite(lin.weight.grad).all() and torch.isfinite(x.grad).all()

@@ -1,0 +1,152 @@
+"""Trainer-side library features: schedules, samplers, meters, checkpoint/resume, config, façade."""
+import argparse
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cpd_b200 import PrecisionConfig
+from cpd_b200.config import add_precision_args
+from cpd_b200.data import (DistributedGivenIterationSampler, GivenIterationSampler, DistributedSampler, Crop, FlipLR, Cutout, Transform,
+                           cifar_shape, PinnedBatchStream, normalise, pad, transpose)
+from cpd_b200.optim import WarmupStepLR, PiecewiseLinear, IterLRScheduler, linear_warmup
+from cpd_b200.utils import AverageMeter, accuracy, save_checkpoint, load_state, make_state, find_latest, JsonlLogger, TableLogger
+
+
+def test_resnet18_schedule_matches_recipe():
+    it_per_epoch = 12
+    s = WarmupStepLR(0.1, 1.6, 5 * it_per_epoch, [40 * it_per_epoch, 80 * it_per_epoch])
+    assert s(0) == pytest.approx(0.1) and s(5 * it_per_epoch) == pytest.approx(1.6)
+    assert s(30) == pytest.approx(0.1 + 1.5 * 30 / 60)
+    assert s(40 * it_per_epoch) == pytest.approx(0.16) and s(80 * it_per_epoch + 1) == pytest.approx(0.016)
+
+
+def test_piecewise_linear_and_iter_scheduler():
+    p = PiecewiseLinear([0, 5, 24], [0, 0.4, 0])
+    assert p(0) == 0 and p(5) == pytest.approx(0.4) and p(24) == 0 and p(2.5) == pytest.approx(0.2)
+    it = IterLRScheduler(0.1, [10, 20], [0.1, 0.5])
+    assert it(5) == pytest.approx(0.1) and it(10) == pytest.approx(0.01) and it(25) == pytest.approx(0.005)
+    assert [it.step() for _ in range(3)] == [pytest.approx(0.1)] * 3
+    assert linear_warmup(1.0, 5, 10) == 0.5 and linear_warmup(1.0, 11, 10) == 1.0
+
+
+def test_given_iteration_samplers_partition_and_resume():
+    ds = list(range(103))
+    full = [list(DistributedGivenIterationSampler(ds, 7, 4, world_size=3, rank=r)) for r in range(3)]
+    assert all(len(x) == 28 for x in full)
+    a = DistributedGivenIterationSampler(ds, 7, 4, world_size=3, rank=1, last_iter=2)
+    assert list(a) == full[1][12:]
+    with pytest.raises(RuntimeError):
+        list(a)
+    g = list(GivenIterationSampler(ds, 5, 8))
+    assert len(g) == 40 and set(g) <= set(range(103))
+    s0, s1 = DistributedSampler(ds, world_size=2, rank=0), DistributedSampler(ds, world_size=2, rank=1)
+    assert len(list(s0)) == len(list(s1)) == 52 and set(list(s0)) | set(list(s1)) == set(range(103))
+    s0.set_epoch(1)
+    assert list(s0) != list(DistributedSampler(ds, world_size=2, rank=0))
+
+
+def test_augmentations_and_preprocessing():
+    raw = np.random.randint(0, 255, (10, 32, 32, 3)).astype(np.uint8)
+    x = transpose(normalise(pad(raw, 4)))
+    assert x.shape == (10, 3, 40, 40) and x.dtype == np.float32
+    t = Transform(list(zip(x, range(10))), [Crop(32, 32), FlipLR(), Cutout(8, 8)])
+    t.set_random_choices()
+    img, label = t[3]
+    assert img.shape == (3, 32, 32) and label == 3 and (img == 0).sum() >= 3 * 64
+    ds = cifar_shape(64)
+    assert ds[0][0].shape == (3, 32, 32) and len(ds) == 64
+    st = PinnedBatchStream(4, pin=False)
+    assert next(st)[0].shape == (4, 3, 32, 32) and st.bytes_per_batch == 4 * 3 * 32 * 32 * 4 + 4 * 8
+
+
+def test_meters_and_accuracy():
+    m = AverageMeter(3)
+    for v in (1, 2, 3, 4):
+        m.update(v)
+    assert m.avg == 3 and m.val == 4
+    g = AverageMeter()
+    g.update(2, 2); g.update(4, 2)
+    assert g.avg == 3
+    out = torch.tensor([[0.1, 0.9, 0.0], [0.8, 0.1, 0.1], [0.2, 0.3, 0.5]])
+    top1, top2 = accuracy(out, torch.tensor([1, 1, 2]), topk=(1, 2))
+    assert top1.item() == pytest.approx(200 / 3) and top2.item() == pytest.approx(100.0)
+
+
+def test_checkpoint_save_resume_reproduces_next_step(tmp_path):
+    from cpd_b200.train import TrainEngine
+    torch.manual_seed(0)
+    def make():
+        torch.manual_seed(0)
+        m = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(48, 16), torch.nn.ReLU(), torch.nn.Linear(16, 10))
+        return TrainEngine(m, PrecisionConfig(grad_exp=5, grad_man=2, use_aps=True), batch_size=4, input_shape=(3, 4, 4), lr=0.05,
+                           use_lars=False, cuda_graph=False)
+    x, y = torch.randn(4, 3, 4, 4), torch.randint(0, 10, (4,))
+    a = make()
+    for _ in range(3):
+        a.train_step(x, y)
+    path = str(tmp_path / "ckpt_3.pth")
+    save_checkpoint(make_state(a.model, a.optimizer, step=3, precision=a.cfg), path, is_best=True)
+    nxt = a.train_step(x, y)
+    b = make()
+    best, last = load_state(path, b.model, b.optimizer)
+    assert last == 3 and os.path.exists(str(tmp_path / "ckpt_best.pth"))
+    assert b.train_step(x, y) == pytest.approx(nxt, rel=1e-6)
+    assert torch.equal(a.arena.model_flat, b.arena.model_flat)
+    assert find_latest(str(tmp_path / "ckpt_*.pth")) == path
+    # module. prefix fix-up
+    sd = {"state_dict": {"module." + k: v for k, v in a.model.state_dict().items()}, "step": 9}
+    torch.save(sd, str(tmp_path / "m.pth"))
+    assert load_state(str(tmp_path / "m.pth"), b.model)[1] == 9
+
+
+def test_config_flags_accept_both_spellings():
+    p = argparse.ArgumentParser()
+    add_precision_args(p)
+    a = p.parse_args(["--use-APS", "--grad_exp", "4", "--grad-man", "3", "--emulate-node", "8", "--use_kahan"])
+    c = PrecisionConfig.from_args(a)
+    assert (c.grad_exp, c.grad_man, c.use_aps, c.use_kahan, c.emulate_node) == (4, 3, True, True, 8)
+    b = p.parse_args(["--use_APS", "--emulate_node", "2"])
+    assert PrecisionConfig.from_args(b).emulate_node == 2
+    with pytest.raises(ValueError):
+        PrecisionConfig(grad_exp=9)
+
+
+def test_cpdtorch_facade_imports():
+    from CPDtorch.quant import float_quantize, quantizer, Quantizer, quant_gemm, Quant_Linear, Quant_Conv  # noqa: F401
+    from CPDtorch.utils.dist_util import dist_init, DistModule, sum_gradients, normal_sum_gradients, kahan_sum_gradients, broadcast_params  # noqa: F401
+    assert float_quantize(torch.tensor([1.06]), 4, 3).item() == 1.0
+
+
+def test_loggers(tmp_path, capsys):
+    j = JsonlLogger(str(tmp_path / "log.jsonl"))
+    j.log(step=1, loss=0.5)
+    j.close()
+    assert '"loss": 0.5' in open(tmp_path / "log.jsonl").read()
+    t = TableLogger()
+    t.append({"epoch": 1, "loss": 0.25})
+    assert "epoch" in capsys.readouterr().out
+
+
+def test_emulate_node_equals_multi_rank_fold():
+    """emulate_node=E on one process == the W=E fold of the same micro-gradients (bitwise)."""
+    from cpd_b200.parallel import ModelArena, EmulateNode
+    from cpd_b200.ops import native
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(12, 9), torch.nn.Tanh(), torch.nn.Linear(9, 3))
+    arena = ModelArena(list(net.parameters()))
+    cfg = PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, emulate_node=4)
+    em = EmulateNode(arena, cfg)
+    xs = [torch.randn(5, 12) for _ in range(4)]
+    micro = []
+    for k in range(4):
+        em.begin_micro(k)
+        (net(xs[k]).square().mean() / 4).backward()
+        micro.append(em.slots[k].clone())
+    em.fold()
+    want = torch.empty(arena.layout.total)
+    native.aps_fold(micro, want, arena.layout.table("cpu").seg_off, 4, 3, True, False, 4.0)
+    assert torch.equal(arena.grad_flat, want)
+    assert net[0].weight.grad.data_ptr() == arena.grad_views[0].data_ptr()
