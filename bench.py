@@ -13,6 +13,8 @@ init of the named architecture (no network on the box).
 """
 from __future__ import annotations
 
+import faulthandler
+
 import argparse
 import json
 import os
@@ -235,6 +237,9 @@ def run_reference(args, cfg):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+faulthandler.enable()
 
 
 def main():

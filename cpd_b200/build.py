@@ -114,14 +114,16 @@ def build(force: bool = False, verbose: bool = True) -> Path:
 
     out = so_path()
     link_stamp = BUILD / "link.hash"
-    digest = hashlib.sha256(b"".join(o.with_suffix(".hash").read_bytes() for o in objs)).hexdigest()
+    digest = hashlib.sha256(b"".join(o.with_suffix(".hash").read_bytes() for o in objs) + b"link-v2").hexdigest()
     if force or not out.exists() or not link_stamp.exists() or link_stamp.read_text() != digest:
         if verbose:
             print(f"[cpd_b200.build] linking {out.name}", flush=True)
         # static CUDA runtime (nvcc's own default): the kernels were built by this toolkit, and the
         # library must not depend on which libcudart the host framework happens to have loaded
+        # -Bsymbolic + --exclude-libs: the static runtime's cuda* symbols stay private to this library, so
+        # they can neither interpose nor be interposed by the libcudart that PyTorch / NCCL loaded
         link = [cxx, "-shared", "-o", str(out), *map(str, objs), f"-L{cuda_home}/lib64", "-lcudart_static", "-lrt",
-                "-ldl", "-lpthread"]
+                "-ldl", "-lpthread", "-Wl,-Bsymbolic", "-Wl,--exclude-libs,ALL"]
         r = subprocess.run(link, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -14,6 +14,8 @@ Device-timed with CUDA events, max over ranks.
 """
 from __future__ import annotations
 
+import faulthandler
+
 import argparse
 import json
 import os
@@ -216,6 +218,9 @@ def section_sweep(rank, world, res, max_bytes):
         del arena
         torch.cuda.empty_cache()
     res["sweep"] = rows
+
+
+faulthandler.enable()
 
 
 def main():
