@@ -175,7 +175,7 @@ __device__ __forceinline__ void wait_peers(const ArParams& p, int phase, unsigne
 }
 
 template <class F, int WIRE, bool KAHAN>
-__global__ void __launch_bounds__(kArThreads)
+__global__ void __launch_bounds__(kArThreads, 2)
 allreduce_fused_kernel(const ArParams p, const F fmt) {
   __shared__ unsigned red[32];
   __shared__ int s_shift[kArMaxT];
@@ -353,7 +353,9 @@ void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunk
   p.ident = (e == 8 && m == 23 && !kahan) ? 1 : 0;
   p.ws = local_ws; p.shifts_out = shifts_out; p.timeout = timeout_cycles;
   if (p.algo == ALGO_NVLS && !cb.mc_gather) p.algo = ALGO_TWOSHOT;
-  int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1);
+  // two co-resident CTAs per SM (<= 128 registers by launch bounds): 16 warps / SM keep enough 128-bit
+  // loads in flight to cover HBM / NVLink latency; the grid barrier needs all CTAs resident
+  int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1) * 2;
   if (grid > n_chunks) grid = n_chunks;
 
 #define CPD_AR_LAUNCH(WIRE_)                                                                          \

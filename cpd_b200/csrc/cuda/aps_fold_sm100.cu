@@ -23,13 +23,22 @@ constexpr int kMaxLocalSrc = 16;
 
 struct SrcPtrs { const float* p[kMaxLocalSrc]; };
 
+// Each thread owns up to kVecPerThread float4 vectors of a chunk, strided by the block size so a
+// warp touches 512 contiguous bytes per vector; all of a thread's loads for one source are issued
+// before the first use (4 x 16 B in flight per thread per source) — the kernel is latency-bound
+// otherwise (Little: 148 SMs x resident warps x bytes in flight / ~1 us DRAM latency).
+constexpr int kVecPerThread = 4;     // 4 x 256 threads x 4 floats = 4096 = CHUNK_ELEMS
+
 template <class F, bool KAHAN>
-__global__ void __launch_bounds__(kFoldThreads)
+__global__ void __launch_bounds__(kFoldThreads, 4)
 aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__ chunks,
                       int n_chunks, int T, int T_cap, F fmt, bool use_aps, float world_mult,
                       unsigned* __restrict__ ws, int* __restrict__ shifts_out) {
   // ws layout: [0]=barrier count, [1]=barrier generation, [2]=launch counter, [4 .. 4+2*T_cap) = amax[2][T_cap]
   __shared__ unsigned red[32];
+  __shared__ const float* s_src[kMaxLocalSrc];
+  if (threadIdx.x < kMaxLocalSrc) s_src[threadIdx.x] = srcs.p[threadIdx.x];
+  __syncthreads();
   unsigned* bar = ws;
   const unsigned launch = ws[2];
   unsigned* amax = ws + 4 + (launch & 1u) * T_cap;
@@ -38,12 +47,19 @@ aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__
   if (use_aps) {
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
       const Chunk ck = chunks[c];
+      const int nvec = ck.len >> 2;
       unsigned m = 0u;
-      for (int i = threadIdx.x * 4; i < ck.len; i += kFoldThreads * 4) {
-        for (int r = 0; r < W; ++r) {
-          const uint4 x = *reinterpret_cast<const uint4*>(srcs.p[r] + ck.start + i);
-          m = max(max(m, x.x & 0x7FFFFFFFu), max(x.y & 0x7FFFFFFFu, max(x.z & 0x7FFFFFFFu, x.w & 0x7FFFFFFFu)));
+      for (int r = 0; r < W; ++r) {
+        const uint4* base = reinterpret_cast<const uint4*>(s_src[r] + ck.start);
+        uint4 x[kVecPerThread];
+#pragma unroll
+        for (int k = 0; k < kVecPerThread; ++k) {
+          const int v = threadIdx.x + k * kFoldThreads;
+          x[k] = v < nvec ? base[v] : make_uint4(0u, 0u, 0u, 0u);
         }
+#pragma unroll
+        for (int k = 0; k < kVecPerThread; ++k)
+          m = max(max(m, x[k].x & 0x7FFFFFFFu), max(x[k].y & 0x7FFFFFFFu, max(x[k].z & 0x7FFFFFFFu, x[k].w & 0x7FFFFFFFu)));
       }
       m = block_max_u32(m, red);
       if (threadIdx.x == 0 && m) atomicMax(&amax[ck.tensor], m);
@@ -53,6 +69,7 @@ aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__
 
   for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const Chunk ck = chunks[c];
+    const int nvec = ck.len >> 2;
     int shift = 0;
     if (use_aps) {
       const unsigned ab = amax[ck.tensor];
@@ -61,29 +78,47 @@ aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__
       if (shifts_out && threadIdx.x == 0) shifts_out[ck.tensor] = shift;
     }
     const float sc = pow2i(shift), inv = pow2i(-shift);
-    for (int i = threadIdx.x * 4; i < ck.len; i += kFoldThreads * 4) {
-      float s[4] = {0.f, 0.f, 0.f, 0.f}, cc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int r = 0; r < W; ++r) {
-        const float4 g4 = *reinterpret_cast<const float4*>(srcs.p[r] + ck.start + i);
-        float g[4] = {g4.x, g4.y, g4.z, g4.w};
+    float s[kVecPerThread][4], cc[KAHAN ? kVecPerThread : 1][4];
+#pragma unroll
+    for (int k = 0; k < kVecPerThread; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[k][j] = 0.f; if (KAHAN) cc[KAHAN ? k : 0][j] = 0.f; }
+    for (int r = 0; r < W; ++r) {
+      const float4* base = reinterpret_cast<const float4*>(s_src[r] + ck.start);
+      float4 g4[kVecPerThread];
+#pragma unroll
+      for (int k = 0; k < kVecPerThread; ++k) {
+        const int v = threadIdx.x + k * kFoldThreads;
+        g4[k] = v < nvec ? base[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < kVecPerThread; ++k) {
+        const float g[4] = {g4[k].x, g4[k].y, g4[k].z, g4[k].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float v = g[j];
           if (use_aps) v = fmt.q(v * sc);
-          if (KAHAN) fold_kahan(fmt, s[j], cc[j], v);
-          else fold_plain(fmt, s[j], v);
+          if (KAHAN) fold_kahan(fmt, s[k][j], cc[KAHAN ? k : 0][j], v);
+          else fold_plain(fmt, s[k][j], v);
         }
       }
-      float4 o;
-      if (use_aps) { o.x = s[0] * inv; o.y = s[1] * inv; o.z = s[2] * inv; o.w = s[3] * inv; }
-      else { o.x = s[0]; o.y = s[1]; o.z = s[2]; o.w = s[3]; }
-      *reinterpret_cast<float4*>(out + ck.start + i) = o;
+    }
+    float4* obase = reinterpret_cast<float4*>(out + ck.start);
+#pragma unroll
+    for (int k = 0; k < kVecPerThread; ++k) {
+      const int v = threadIdx.x + k * kFoldThreads;
+      if (v < nvec) {
+        float4 o;
+        if (use_aps) { o.x = s[k][0] * inv; o.y = s[k][1] * inv; o.z = s[k][2] * inv; o.w = s[k][3] * inv; }
+        else { o.x = s[k][0]; o.y = s[k][1]; o.z = s[k][2]; o.w = s[k][3]; }
+        obase[v] = o;
+      }
     }
   }
 
   // prepare the other amax buffer for the next launch and bump the launch counter.
   // Safe without another barrier: nobody touches amax_next in this launch, and ws[2]
-  // was read by every CTA before the grid barrier (use_aps) or is only parity for amax.
+  // was read by every CTA before the grid barrier.
   if (use_aps && blockIdx.x == 0) {
     for (int t = threadIdx.x; t < T_cap; t += kFoldThreads) amax_next[t] = 0u;
     __syncthreads();
@@ -97,7 +132,7 @@ void aps_fold_local_cuda(const float* const* srcs_host, int W, float* out, const
   if (n_chunks <= 0 || W <= 0) return;
   SrcPtrs sp;
   for (int r = 0; r < kMaxLocalSrc; ++r) sp.p[r] = r < W ? srcs_host[r] : nullptr;
-  int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1) * 2;
+  int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1) * 4;   // 4 co-resident CTAs / SM (launch bounds)
   if (grid > n_chunks) grid = n_chunks;
   CPD_DISPATCH_FORMAT(e, m, ROUND_REF, FMT, {
     if (kahan)

@@ -19,8 +19,9 @@
 namespace cpd {
 
 constexpr int kLarsThreads = 256;
+constexpr int kVec = 4;              // float4 vectors per thread per chunk (4 x 256 x 4 = 4096 elements)
 
-__global__ void __launch_bounds__(kLarsThreads)
+__global__ void __launch_bounds__(kLarsThreads, 3)
 lars_kernel(float* master, float* model, const float* __restrict__ grad, float* mom,
             const Chunk* __restrict__ chunks, const int* __restrict__ tchunk_off, int n_chunks, int T,
             const float* __restrict__ lr_dev, float lr_host, float momentum, float wd, float coeff,
@@ -34,11 +35,22 @@ lars_kernel(float* master, float* model, const float* __restrict__ grad, float* 
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
       const Chunk ck = chunks[c];
       float w2 = 0.f, g2 = 0.f;
-      for (int i = threadIdx.x * 4; i < ck.len; i += kLarsThreads * 4) {
-        const float4 w = *reinterpret_cast<const float4*>(master + ck.start + i);
-        const float4 g = *reinterpret_cast<const float4*>(grad + ck.start + i);
-        w2 += w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w;
-        g2 += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+      {
+        const int nvec = ck.len >> 2;
+        const float4* wb = reinterpret_cast<const float4*>(master + ck.start);
+        const float4* gb = reinterpret_cast<const float4*>(grad + ck.start);
+        float4 w[kVec], g[kVec];
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) {      // all loads first: 8 x 16 B in flight per thread
+          const int v = threadIdx.x + k * kLarsThreads;
+          w[k] = v < nvec ? wb[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+          g[k] = v < nvec ? gb[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) {
+          w2 += w[k].x * w[k].x + w[k].y * w[k].y + w[k].z * w[k].z + w[k].w * w[k].w;
+          g2 += g[k].x * g[k].x + g[k].y * g[k].y + g[k].z * g[k].z + g[k].w * g[k].w;
+        }
       }
       w2 = block_sum_f32(w2, red);
       g2 = block_sum_f32(g2, red);
@@ -69,28 +81,41 @@ lars_kernel(float* master, float* model, const float* __restrict__ grad, float* 
       __syncthreads();
       local_lr = s_local_lr;
     }
-    for (int i = threadIdx.x * 4; i < ck.len; i += kLarsThreads * 4) {
-      const long long o = ck.start + i;
-      const float4 w4 = *reinterpret_cast<const float4*>(master + o);
-      const float4 g4 = *reinterpret_cast<const float4*>(grad + o);
-      const float4 b4 = *reinterpret_cast<const float4*>(mom + o);
-      float w[4] = {w4.x, w4.y, w4.z, w4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+    {
+      const int nvec = ck.len >> 2;
+      float4* wb = reinterpret_cast<float4*>(master + ck.start);
+      const float4* gb = reinterpret_cast<const float4*>(grad + ck.start);
+      float4* bb = reinterpret_cast<float4*>(mom + ck.start);
+      float4* mb = model ? reinterpret_cast<float4*>(model + ck.start) : nullptr;
+      float4 w4[kVec], g4[kVec], b4[kVec];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float d = g[j] + wdt * w[j];
-        float upd;
-        if (use_lars) {
-          b[j] = momentum * b[j] + lr * local_lr * d;
-          upd = b[j];
-        } else {
-          b[j] = momentum * b[j] + d;
-          upd = lr * (nesterov ? d + momentum * b[j] : b[j]);
-        }
-        w[j] = w[j] - upd;
+      for (int k = 0; k < kVec; ++k) {        // 12 x 16 B in flight per thread
+        const int v = threadIdx.x + k * kLarsThreads;
+        if (v < nvec) { w4[k] = wb[v]; g4[k] = gb[v]; b4[k] = bb[v]; }
       }
-      *reinterpret_cast<float4*>(mom + o) = make_float4(b[0], b[1], b[2], b[3]);
-      *reinterpret_cast<float4*>(master + o) = make_float4(w[0], w[1], w[2], w[3]);
-      if (model) *reinterpret_cast<float4*>(model + o) = make_float4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+      for (int k = 0; k < kVec; ++k) {
+        const int v = threadIdx.x + k * kLarsThreads;
+        if (v >= nvec) continue;
+        float w[4] = {w4[k].x, w4[k].y, w4[k].z, w4[k].w}, g[4] = {g4[k].x, g4[k].y, g4[k].z, g4[k].w};
+        float b[4] = {b4[k].x, b4[k].y, b4[k].z, b4[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float d = g[j] + wdt * w[j];
+          float upd;
+          if (use_lars) {
+            b[j] = momentum * b[j] + lr * local_lr * d;
+            upd = b[j];
+          } else {
+            b[j] = momentum * b[j] + d;
+            upd = lr * (nesterov ? d + momentum * b[j] : b[j]);
+          }
+          w[j] = w[j] - upd;
+        }
+        bb[v] = make_float4(b[0], b[1], b[2], b[3]);
+        wb[v] = make_float4(w[0], w[1], w[2], w[3]);
+        if (mb) mb[v] = make_float4(w[0], w[1], w[2], w[3]);
+      }
     }
     if (use_lars) __syncthreads();   // s_local_lr is rewritten by the next chunk
   }
@@ -102,7 +127,7 @@ void lars_step_cuda(float* master, float* model, const float* grad, float* mom, 
                     const float* wd_mult, float* partials, unsigned* barrier_ws, int max_ctas,
                     cudaStream_t st) {
   if (n_chunks <= 0) return;
-  int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1) * 2;
+  int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1) * 3;
   if (grid > n_chunks) grid = n_chunks;
   lars_kernel<<<grid, kLarsThreads, 0, st>>>(master, model, grad, mom, chunks, tchunk_off, n_chunks, T,
                                               lr_dev, lr, momentum, wd, coeff, eps, use_lars, nesterov,
