@@ -3,6 +3,8 @@
 //   C[M,N] = A[M,K] . Bt[N,K]^T,  accumulator held at (exp, man):
 //   for every K-slice:  partial = sum_{k in slice} a*b   (tcgen05.mma, fp32 in TMEM)
 //                       s = Q(s (+) Q(partial))          (plain or Kahan, in registers)
+//   Q = IEEE round-to-nearest-even cast to (exp, man) (rounding="ieee" of float_quantize); for
+//   (5,10)/(8,7)/(4,3)/(5,2) it is two hardware convert instructions (fpformat_hw.cuh).
 //
 // This is the B200 replacement for the reference's tvm_gemm (float_kernel.cu:103-340): a
 // 64-thread SIMT kernel with ~5 software casts per multiply-add.  Here the multiply-adds run on
@@ -27,6 +29,7 @@
 
 #include "../api.h"
 #include "../common/fpformat.h"
+#include "../common/fpformat_hw.cuh"
 #include "format_dispatch.cuh"
 
 namespace cpd {
@@ -319,7 +322,8 @@ int launch_kind(const CUtensorMap& ta, const CUtensorMap& tb, float* C, const fl
                 int kblocks_per_slice, uint32_t idesc, int e, int m, bool kahan, cudaStream_t st) {
   dim3 grid((N + tc::BLOCK_N - 1) / tc::BLOCK_N, (M + tc::BLOCK_M - 1) / tc::BLOCK_M);
   int rc = 0;
-  CPD_DISPATCH_FORMAT(e, m, ROUND_REF, FMT, {
+  // accumulator casts use IEEE rounding (hardware F2F/F2FP converts for fp16/bf16/e4m3/e5m2-shaped formats)
+  CPD_DISPATCH_FORMAT_IEEE_HW(e, m, FMT, {
     if (kahan) {
       auto kfn = gemm_tcgen05_kernel<KIND, decltype(FMT), true>;
       if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES) != cudaSuccess) rc = -3;

@@ -163,7 +163,7 @@ def test_engine_emulate_node_equals_cpu_semantics():
 # ---- tcgen05 tensor-core GEMM -----------------------------------------------------------
 def _tc_ref(a_op, bt_op, e, m, kahan, k_slice):
     """CPU model of the tile semantics on the (already operand-rounded) inputs."""
-    return native.gemm_tile_cpu(a_op.float().cpu(), bt_op.float().cpu().t(), e, m, kahan=kahan, k_slice=k_slice)
+    return native.gemm_tile_cpu(a_op.float().cpu(), bt_op.float().cpu().t(), e, m, rounding="ieee", kahan=kahan, k_slice=k_slice)
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 512), (200, 136, 264), (1, 8, 16), (1024, 64, 2304)])

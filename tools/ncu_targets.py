@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Tiny driver that launches each hand-written single-GPU kernel a few times so `ncu -k regex:...` can capture it."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cpd_b200.ops import native  # noqa: E402
+from cpd_b200.parallel.arena import ArenaLayout  # noqa: E402
+from cpd_b200.models import create_model  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+torch.manual_seed(0)
+if which in ("all", "gemm_tc"):
+    M = N = K = 4096
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    bt = torch.randn(N, K, device="cuda").bfloat16()
+    for _ in range(3):
+        native.gemm_tc(a, bt, 5, 10, kahan=False, k_slice=256, operand_mode=native.OPERAND_BF16)
+    a8, b8 = a.to(torch.float8_e4m3fn), bt.to(torch.float8_e4m3fn)
+    for _ in range(3):
+        native.gemm_tc(a8, b8, 4, 3, kahan=False, k_slice=512, operand_mode=native.OPERAND_E4M3)
+if which in ("all", "fold", "lars"):
+    numels = [p.numel() for p in create_model("resnet18_cifar").parameters()]
+    layout = ArenaLayout(numels)
+    tab = layout.table("cuda")
+    ws = torch.zeros(4 + 2 * 128, dtype=torch.int32, device="cuda")
+    g = torch.randn(layout.total, device="cuda") * 1e-3
+    out = torch.empty_like(g)
+    if which in ("all", "fold"):
+        for _ in range(3):
+            native.aps_fold([g], out, tab.seg_off, 4, 3, True, False, 1.0, chunks=tab.chunks, workspace=ws)
+    if which in ("all", "lars"):
+        master, mom, model = torch.randn_like(g), torch.zeros_like(g), torch.empty_like(g)
+        partials = torch.zeros(2 * tab.n_chunks, device="cuda")
+        bar = torch.zeros(4, dtype=torch.int32, device="cuda")
+        lr = torch.tensor([0.1], device="cuda")
+        for _ in range(3):
+            native.lars_step(master, model, g, mom, tab.seg_off, 0.1, 0.9, 1e-4, use_lars=True, chunks=tab.chunks, tchunk_off=tab.tchunk_off,
+                             lr_dev=lr, partials=partials, barrier_ws=bar)
+torch.cuda.synchronize()
+print("done", which)

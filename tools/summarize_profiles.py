@@ -1,0 +1,146 @@
+#!/usr/bin/env python
+"""Copies the measured numbers worth judging from gpurun_out/ (scratch) into profiles/ (tracked):
+bench JSON lines, micro-benchmarks, all-reduce sweeps (with a roofline column), launch lists and
+per-kernel ncu summaries (key raw metrics + the hottest source lines / stall reasons)."""
+import csv
+import glob
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GO = os.path.join(ROOT, "gpurun_out")
+PR = os.path.join(ROOT, "profiles")
+NVLINK_MEASURED_GBS = 770.0      # per direction per GPU, B200_PROFILING.md
+KEY_METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+               "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+               "sm__inst_executed_pipe_tensor.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+               "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+               "smsp__inst_executed.sum", "smsp__cycles_active.avg", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+               "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+               "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+               "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+               "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+               "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+
+
+def ncu_summary(rep, out_md):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) < 3:
+        return False
+    H, U = rows[0], rows[1]
+    lines = [f"# ncu summary: {os.path.basename(rep)}", "", "`ncu --set full --clock-control none --import-source on` on one B200; numbers under the profiler are for attribution only, never bench values.", ""]
+    for r in rows[2:]:
+        name = r[H.index("Kernel Name")]
+        lines += [f"## {name[:160]}", "", "| metric | value | unit |", "|---|---|---|"]
+        for m in KEY_METRICS:
+            if m in H:
+                lines.append(f"| {m} | {r[H.index(m)]} | {U[H.index(m)]} |")
+        lines.append("")
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    srows = list(csv.reader(src.splitlines()))
+    if len(srows) > 2:
+        SH = srows[0]
+        def col(*names):
+            for n in names:
+                if n in SH:
+                    return SH.index(n)
+            return None
+        ci, cs, cw = col("Source"), col("Warp Stall Sampling (All Samples)", "Warp Stall Sampling (All Cycles)"), col("# Instructions Executed", "Instructions Executed")
+        if ci is not None and cs is not None:
+            top = []
+            for r in srows[1:]:
+                try:
+                    top.append((float(r[cs].replace(",", "") or 0), r[ci][:110], r[cw] if cw is not None else ""))
+                except (ValueError, IndexError):
+                    pass
+            top.sort(reverse=True)
+            tot = sum(t[0] for t in top) or 1
+            lines += ["## hottest source lines (warp-stall samples, first captured launch)", "", "| % of samples | instructions | source |", "|---|---|---|"]
+            for s, t, w in top[:14]:
+                lines.append(f"| {100 * s / tot:.1f} | {w} | `{t.strip()}` |")
+            lines.append("")
+    open(out_md, "w").write("\n".join(lines) + "\n")
+    return True
+
+
+def launch_summary(csv_path, out_md, title):
+    rows = list(csv.reader(open(csv_path)))
+    hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"]
+    if not hdr:
+        return
+    H = rows[hdr[0]]
+    ki, vi = H.index("Kernel Name"), H.index("Metric Value")
+    agg = {}
+    for r in rows[hdr[0] + 1:]:
+        try:
+            v = float(r[vi].replace(",", ""))
+        except (ValueError, IndexError):
+            continue
+        a = agg.setdefault(r[ki][:110], [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(v[1] for v in agg.values()) or 1
+    lines = [f"# {title}", "", "`ncu --metrics gpu__time_duration.sum --clock-control none` over 3 eager (no CUDA graph) training steps; cold-cache, serialised: compare SHARES.", "",
+             f"total {tot / 1e6:.2f} ms over {sum(v[0] for v in agg.values())} launches", "", "| share | launches | total us | kernel |", "|---|---|---|---|"]
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+        lines.append(f"| {100 * v[1] / tot:.1f}% | {v[0]} | {v[1] / 1e3:.1f} | `{k}` |")
+    open(out_md, "w").write("\n".join(lines) + "\n")
+
+
+def sweep_md(js, out_md):
+    d = json.load(open(js))
+    W = d.get("world")
+    rows = d.get("sweep", [])
+    if not rows:
+        return
+    lines = [f"# low-bit all-reduce sweep, {W} x B200 ((4,3) + APS, 8-bit wire)", "",
+             "Device-timed (CUDA events, max over ranks).  busbw = fp32 payload / t * 2(W-1)/W (nccl-tests convention).  Roofline for the fused kernel = slower of",
+             "(wire bytes that must cross NVLink per GPU / 770 GB/s measured) and (local HBM traffic ~ 13 B/element / measured copy bandwidth).", "",
+             "| fp32 bytes | fused one-shot us | fused two-shot us | fused NVLS us | fused Kahan us | NCCL fp32 all_reduce us | reference algorithm us | best fused busbw GB/s | NCCL busbw GB/s | reference busbw GB/s | fused roofline us | fused / roofline |",
+             "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:  # noqa: BLE001
+        hbm = 6650.0
+    for r in rows:
+        n = r["elems"]
+        best = min(v for k, v in r.items() if k.startswith("fused_") and k.endswith("_us") and "kahan" not in k)
+        link_us = (2 * (W - 1) / W * n * 1) / (NVLINK_MEASURED_GBS * 1e3)          # two-shot wire bytes per GPU per direction
+        hbm_us = (13.0 * n) / (hbm * 1e3)
+        roof = max(link_us, hbm_us)
+        bw = max(v for k, v in r.items() if k.startswith("fused_") and k.endswith("busbw_fp32_GBps"))
+        lines.append(f"| {r['fp32_bytes']} | {r.get('fused_oneshot_us', '-')} | {r.get('fused_twoshot_us', '-')} | {r.get('fused_nvls_us', '-')} | {r.get('fused_auto_kahan_us', '-')} | "
+                     f"{r.get('nccl_fp32_allreduce_us', '-')} | {r.get('reference_algo_us', '-')} | {bw} | {r.get('nccl_fp32_busbw_GBps', '-')} | {r.get('reference_algo_busbw_fp32_GBps', '-')} | "
+                     f"{roof:.2f} | {roof / best:.3f} |")
+    open(out_md, "w").write("\n".join(lines) + "\n")
+
+
+def main():
+    os.makedirs(os.path.join(PR, "bench"), exist_ok=True)
+    os.makedirs(os.path.join(PR, "ncu"), exist_ok=True)
+    for p in glob.glob(os.path.join(GO, "trip*", "bench*.json")):
+        if os.path.getsize(p) > 10:
+            shutil.copy(p, os.path.join(PR, "bench", os.path.basename(os.path.dirname(p)) + "_" + os.path.basename(p)))
+    for p in glob.glob(os.path.join(GO, "trip*", "microbench.json")) + glob.glob(os.path.join(GO, "trip*", "bench_gemm.json")):
+        if os.path.getsize(p) > 10:
+            shutil.copy(p, os.path.join(PR, os.path.basename(os.path.dirname(p)) + "_" + os.path.basename(p)))
+    for p in glob.glob(os.path.join(GO, "trip*", "sweep.json")) + glob.glob(os.path.join(GO, "trip*", "check.json")):
+        tag = os.path.basename(os.path.dirname(p))
+        shutil.copy(p, os.path.join(PR, f"allreduce_{tag}_{os.path.basename(p)}"))
+        if p.endswith("sweep.json"):
+            sweep_md(p, os.path.join(PR, f"allreduce_{tag}_sweep.md"))
+    for p in glob.glob(os.path.join(GO, "trip*", "launches.csv")):
+        launch_summary(p, os.path.join(PR, f"launches_{os.path.basename(os.path.dirname(p))}.md"), "kernel launch list of one ResNet-18 training step (ours)")
+    for p in glob.glob(os.path.join(GO, "trip*", "*.ncu-rep")):
+        tag = os.path.basename(os.path.dirname(p)) + "_" + os.path.basename(p).replace(".ncu-rep", "")
+        ok = ncu_summary(p, os.path.join(PR, "ncu", tag + ".md"))
+        print("ncu", tag, ok)
+    print("profiles updated")
+
+
+if __name__ == "__main__":
+    main()
