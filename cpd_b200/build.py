@@ -31,6 +31,7 @@ CUDA_SOURCES = [
     "cuda/lars_sm100.cu",
     "cuda/gemm_exact_sm100.cu",
     "cuda/gemm_tcgen05_sm100a.cu",
+    "cuda/gemm_tcgen05_2cta_sm100a.cu",
     "cuda/allreduce_fused_sm100a.cu",
 ]
 CPP_SOURCES = [

@@ -89,8 +89,12 @@ void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunk
 
 // tcgen05 / TMEM / TMA GEMM with per-K-slice accumulator re-quantisation.
 // operand_mode: 0 = bf16 operands (kind::f16), 1 = tf32 (kind::tf32), 2 = e4m3, 3 = e5m2
+// variant: 0 = auto, 1 = 128x128 single-CTA tiles, 2 = 256x256 CTA-pair tiles (cta_group::2 cluster kernel,
+// packed 16-bit accumulators; formats (5,10), (8,7), (4,3), (5,2) only)
 int gemm_tc_cuda(const void* A, const void* B, float* C, int M, int N, int K, int e, int m,
-                 bool kahan, int k_slice, int operand_mode, const float* bias, cudaStream_t st);
+                 bool kahan, int k_slice, int operand_mode, const float* bias, int variant, cudaStream_t st);
+int gemm_tc2_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, int e, int m, bool kahan, int k_slice,
+                  int operand_mode, const float* bias, cudaStream_t st);
 #endif
 
 }  // namespace cpd

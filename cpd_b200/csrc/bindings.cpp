@@ -78,10 +78,10 @@ PYBIND11_MODULE(_C, m) {
   });
   // A [M,K] row-major, Bt [N,K] row-major (both K-major); operand_mode 0 bf16, 1 tf32(fp32 in), 2 e4m3, 3 e5m2
   m.def("gemm_tc_cuda", [](uptr A, uptr Bt, uptr C, int M, int N, int K, int e, int mb, bool kahan, int k_slice,
-                           int operand_mode, uptr bias, uptr stream) {
+                           int operand_mode, uptr bias, int variant, uptr stream) {
     check_fmt(e, mb);
     int rc = cpd::gemm_tc_cuda(P<const void>(A), P<const void>(Bt), P<float>(C), M, N, K, e, mb, kahan, k_slice, operand_mode,
-                               P<const float>(bias), S(stream));
+                               P<const float>(bias), variant, S(stream));
     check_launch("gemm_tc");
     return rc;
   });

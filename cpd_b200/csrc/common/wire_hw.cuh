@@ -1,0 +1,89 @@
+// wire_hw.cuh — hardware-assisted wire codec and fold cast for the 8-bit formats.
+//
+// The reference-exact cast has two quirks that IEEE converts do not reproduce:
+// A (overflow tested before rounding) and B (truncating shift for target subnormals).  Inside the
+// all-reduce fold, however, every value that is cast is an exact fp32 sum or difference of two
+// MEMBERS of the format (multiples of its subnormal quantum), so a subnormal result needs no
+// rounding at all and quirk B cannot trigger; quirk A only concerns |x| >= 2^(emax+1) - ulp/2.
+// Hence for |x| below that bound the reference cast == the IEEE cast == Blackwell's
+// F2FP.SATFINITE.{E4M3,E5M2} convert, and CPD-(4,3)/(5,2) codes below the all-ones exponent are
+// bit-identical to OCP E4M3/E5M2 codes.  Everything else (NaN, Inf, the quirk band, reserved
+// codes) takes the exact software path.  Result: bit-exact with the software implementation at
+// ~1/3 of the instructions.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
+#include "fpformat.h"
+
+namespace cpd {
+
+// ---- generic (software) operations ----------------------------------------------------
+template <class F>
+struct FoldOps {
+  static constexpr bool kHw = false;
+  static __device__ __forceinline__ float qsum(const F& f, float x) { return f.q(x); }
+  static __device__ __forceinline__ void decode4(const F& f, uint32_t w, float (&o)[4]) {
+    o[0] = f.unpack(w & 0xFFu); o[1] = f.unpack((w >> 8) & 0xFFu); o[2] = f.unpack((w >> 16) & 0xFFu); o[3] = f.unpack(w >> 24);
+  }
+  static __device__ __forceinline__ uint32_t encode4(const F& f, const float (&x)[4]) {
+    return f.pack(x[0]) | (f.pack(x[1]) << 8) | (f.pack(x[2]) << 16) | (f.pack(x[3]) << 24);
+  }
+};
+
+// ---- hardware paths -------------------------------------------------------------------------
+template <int E_BITS, int M_BITS, __nv_fp8_interpretation_t INTERP>
+struct FoldOpsFp8 {
+  using F = FmtT<E_BITS, M_BITS>;
+  static constexpr bool kHw = true;
+  static constexpr int bias = (1 << (E_BITS - 1)) - 1;
+  // first magnitude that must NOT take the hardware path: 2^(emax+1) - half ulp of the top binade
+  static constexpr float kLimit = (E_BITS == 4) ? 248.0f : 61440.0f;
+  static constexpr uint32_t kExpMask8 = ((1u << E_BITS) - 1u) << M_BITS;            // exponent bits of one code
+  static constexpr uint32_t kExpMask32 = kExpMask8 * 0x01010101u;
+  static constexpr uint32_t kCarry32 = (1u << M_BITS) * 0x01010101u;               // + this sets bit 7 iff exponent is all ones
+
+  static __device__ __forceinline__ float qsum(const F& f, float x) {
+    if (fabsf(x) < kLimit) {
+      const __nv_fp8_storage_t c = __nv_cvt_float_to_fp8(x, __NV_SATFINITE, INTERP);
+      return __half2float(__half(__nv_cvt_fp8_to_halfraw(c, INTERP)));
+    }
+    return f.q(x);                                    // NaN / Inf / quirk band: exact software cast
+  }
+  static __device__ __forceinline__ void decode4(const F& f, uint32_t w, float (&o)[4]) {
+    if ((((w & kExpMask32) + kCarry32) & 0x80808080u) == 0u) {          // no reserved (all-ones exponent) code among the 4
+      const __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w & 0xFFFFu), INTERP);
+      const __half2_raw hi = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w >> 16), INTERP);
+      const float2 a = __half22float2(__half2(lo)), b = __half22float2(__half2(hi));
+      o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    } else {
+      o[0] = f.unpack(w & 0xFFu); o[1] = f.unpack((w >> 8) & 0xFFu); o[2] = f.unpack((w >> 16) & 0xFFu); o[3] = f.unpack(w >> 24);
+    }
+  }
+  static __device__ __forceinline__ uint32_t encode4(const F& f, const float (&x)[4]) {
+    const float m = fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3])));
+    const bool nan = (x[0] != x[0]) | (x[1] != x[1]) | (x[2] != x[2]) | (x[3] != x[3]);
+    if (m < kLimit && !nan) {                                             // all four are finite members below the reserved range
+      const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(x[0], x[1]), __NV_SATFINITE, INTERP);
+      const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(x[2], x[3]), __NV_SATFINITE, INTERP);
+      return lo | (hi << 16);
+    }
+    return f.pack(x[0]) | (f.pack(x[1]) << 8) | (f.pack(x[2]) << 16) | (f.pack(x[3]) << 24);
+  }
+};
+
+template <> struct FoldOps<FmtT<4, 3>> : FoldOpsFp8<4, 3, __NV_E4M3> {};
+template <> struct FoldOps<FmtT<5, 2>> : FoldOpsFp8<5, 2, __NV_E5M2> {};
+
+// fold steps whose casts act on exact sums / differences of format members (see header comment)
+template <class F>
+__device__ __forceinline__ void fold_plain_members(const F& f, float& s, float v) { s = FoldOps<F>::qsum(f, s + v); }
+template <class F>
+__device__ __forceinline__ void fold_kahan_members(const F& f, float& s, float& c, float v) {
+  const float y = FoldOps<F>::qsum(f, v - c);
+  const float t = FoldOps<F>::qsum(f, s + y);
+  c = FoldOps<F>::qsum(f, FoldOps<F>::qsum(f, t - s) - y);
+  s = t;
+}
+
+}  // namespace cpd

@@ -27,6 +27,7 @@
 #include "../api.h"
 #include "../common/fpformat.h"
 #include "../common/device_utils.cuh"
+#include "../common/wire_hw.cuh"
 #include "format_dispatch.cuh"
 
 namespace cpd {
@@ -106,10 +107,9 @@ __device__ __forceinline__ void granule_decode(const F& fmt, const Granule<WIRE>
     const unsigned w[4] = {g.v[0].x, g.v[0].y, g.v[0].z, g.v[0].w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      x[4 * k + 0] = fmt.unpack(w[k] & 0xFFu);
-      x[4 * k + 1] = fmt.unpack((w[k] >> 8) & 0xFFu);
-      x[4 * k + 2] = fmt.unpack((w[k] >> 16) & 0xFFu);
-      x[4 * k + 3] = fmt.unpack(w[k] >> 24);
+      float o[4];
+      FoldOps<F>::decode4(fmt, w[k], o);          // hardware E4M3/E5M2 unpack where the codes allow it
+      x[4 * k + 0] = o[0]; x[4 * k + 1] = o[1]; x[4 * k + 2] = o[2]; x[4 * k + 3] = o[3];
     }
   }
 }
@@ -132,8 +132,10 @@ __device__ __forceinline__ Granule<WIRE> granule_encode(const F& fmt, const floa
   } else {
     unsigned w[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      w[k] = fmt.pack(x[4 * k]) | (fmt.pack(x[4 * k + 1]) << 8) | (fmt.pack(x[4 * k + 2]) << 16) | (fmt.pack(x[4 * k + 3]) << 24);
+    for (int k = 0; k < 4; ++k) {
+      const float in4[4] = {x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]};
+      w[k] = FoldOps<F>::encode4(fmt, in4);
+    }
     g.v[0] = make_uint4(w[0], w[1], w[2], w[3]);
   }
   return g;
@@ -281,8 +283,10 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
           else granule_decode<WIRE>(fmt, granule_load_sys<WIRE>(p.data[r] + par * p.cap_bytes, e0), v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            if (KAHAN) fold_kahan(fmt, s[i], cc[i], v[i]);
+            // WIRE < 32: every operand is a member of the format -> hardware-assisted exact casts
+            if (KAHAN) { if (WIRE < 32) fold_kahan_members(fmt, s[i], cc[i], v[i]); else fold_kahan(fmt, s[i], cc[i], v[i]); }
             else if (p.ident) s[i] += v[i];
+            else if (WIRE < 32) fold_plain_members(fmt, s[i], v[i]);
             else fold_plain(fmt, s[i], v[i]);
           }
         }

@@ -14,6 +14,7 @@
 #include "../api.h"
 #include "../common/fpformat.h"
 #include "../common/device_utils.cuh"
+#include "../common/wire_hw.cuh"
 #include "format_dispatch.cuh"
 
 namespace cpd {
@@ -97,9 +98,16 @@ aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float v = g[j];
-          if (use_aps) v = fmt.q(v * sc);
-          if (KAHAN) fold_kahan(fmt, s[k][j], cc[KAHAN ? k : 0][j], v);
-          else fold_plain(fmt, s[k][j], v);
+          if (use_aps) {
+            // v becomes a member of the format, so every later cast acts on an exact sum of members:
+            // hardware-assisted exact path for the fp8-shaped formats (wire_hw.cuh)
+            v = fmt.q(v * sc);
+            if (KAHAN) fold_kahan_members(fmt, s[k][j], cc[KAHAN ? k : 0][j], v);
+            else fold_plain_members(fmt, s[k][j], v);
+          } else {
+            if (KAHAN) fold_kahan(fmt, s[k][j], cc[KAHAN ? k : 0][j], v);
+            else fold_plain(fmt, s[k][j], v);
+          }
         }
       }
     }

@@ -140,12 +140,16 @@ def gemm_tile_cpu(a, b, exp, man, rounding=ROUND_REF, kahan=False, k_slice=128, 
 OPERAND_BF16, OPERAND_TF32, OPERAND_E4M3, OPERAND_E5M2 = 0, 1, 2, 3
 
 
+GEMM_AUTO, GEMM_1CTA, GEMM_2CTA = 0, 1, 2
+
+
 def gemm_tc(a: torch.Tensor, bt: torch.Tensor, exp: int, man: int, kahan: bool = False, k_slice: int = 128,
             operand_mode: int = OPERAND_BF16, bias: Optional[torch.Tensor] = None,
-            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, variant: int = GEMM_AUTO) -> torch.Tensor:
     """tcgen05 GEMM: C[M,N] = A[M,K] @ Bt[N,K]^T, accumulator re-quantised to (exp,man)
-    after every K-slice.  Operands must already be in the operand dtype (bf16 / fp32
-    for tf32 / float8)."""
+    (IEEE rounding) after every K-slice.  Operands must already be in the operand dtype (bf16 /
+    fp32 for tf32 / float8).  ``variant``: auto | 128x128 single-CTA tiles | 256x256 CTA-pair
+    (cluster, cta_group::2) tiles with packed 16-bit accumulators."""
     _check_fmt(exp, man)
     if not (a.is_cuda and bt.is_cuda and a.is_contiguous() and bt.is_contiguous()):
         raise ValueError("gemm_tc: contiguous CUDA operands expected")
@@ -161,7 +165,7 @@ def gemm_tc(a: torch.Tensor, bt: torch.Tensor, exp: int, man: int, kahan: bool =
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         rc = _C.gemm_tc_cuda(a.data_ptr(), bt.data_ptr(), out.data_ptr(), M, N, K, int(exp), int(man), bool(kahan),
-                             int(k_slice), int(operand_mode), _ptr(bias), _stream(a))
+                             int(k_slice), int(operand_mode), _ptr(bias), int(variant), _stream(a))
     if rc != 0:
         raise RuntimeError(f"gemm_tc: kernel rejected the problem (code {rc})")
     return out

@@ -91,8 +91,10 @@ def quant_gemm(a: torch.Tensor, b: torch.Tensor, man: int = 23, exp: int = 8, mo
     mode="exact": the reference's semantics — strictly sequential k, every product and
         every (Kahan) intermediate cast; SIMT kernel / C++ on CPU.  Inputs are not cast.
     mode="tile":  B200 throughput path — tcgen05 tensor-core partial sums over ``k_slice``
-        elements of K in fp32 (TMEM), then ``s = Q(s (+) Q(partial))`` per slice; operands
-        are staged as fp8 for (4,3)/(5,2), bf16 for man<=7, tf32 otherwise.
+        elements of K in fp32 (TMEM), then ``s = Q(s (+) Q(partial))`` per slice with IEEE
+        rounding (hardware converts); operands are staged as fp8 for (4,3)/(5,2), bf16 for
+        man<=7, tf32 otherwise.  Large problems in the 16-bit-representable formats run on
+        CTA pairs (thread-block clusters, cta_group::2) with packed 16-bit accumulators.
     mode="auto":  exact on CPU and for small problems, tile otherwise.
     ``kahan`` defaults to True for exact (as the reference) and False for tile.
     """

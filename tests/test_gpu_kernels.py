@@ -216,3 +216,32 @@ def test_quant_gemm_tile_mode_and_linear_tile():
     y = lin(x)
     y.sum().backward()
     assert torch.isfinite(y).all() and torch.isfinite(lin.weight.grad).all() and torch.isfinite(x.grad).all()
+
+
+# ---- CTA-pair (cluster, cta_group::2) variant ---------------------------------------------------------
+@pytest.mark.parametrize("e,m,kahan,k_slice", [(5, 10, False, 128), (5, 10, True, 256), (8, 7, False, 64), (4, 3, False, 128), (5, 2, True, 128)])
+@pytest.mark.parametrize("M,N,K", [(512, 512, 1024), (300, 520, 264), (256, 256, 64), (1000, 260, 4096)])
+def test_gemm_tc_2cta_equals_1cta_and_model(e, m, kahan, k_slice, M, N, K):
+    torch.manual_seed(M + N + K + e)
+    a = (torch.randn(M, K, device="cuda") * 0.25).bfloat16()
+    bt = (torch.randn(N, K, device="cuda") * 0.25).bfloat16()
+    one = native.gemm_tc(a, bt, e, m, kahan=kahan, k_slice=k_slice, variant=native.GEMM_1CTA)
+    two = native.gemm_tc(a, bt, e, m, kahan=kahan, k_slice=k_slice, variant=native.GEMM_2CTA)
+    # same casts (IEEE), same per-slice tensor-core partials -> the two tilings must agree bit for bit
+    assert torch.equal(one, two), float((one - two).abs().max())
+    if M * N * K <= 512 * 512 * 1024:
+        want = _tc_ref(a, bt, e, m, kahan, k_slice)
+        rel = (two.cpu() - want).abs() / want.abs().clamp_min(1e-6)
+        assert float((rel <= 2 * 2.0 ** (-m)).float().mean()) > 0.999
+
+
+def test_gemm_tc_2cta_fp8_operands_and_bias():
+    torch.manual_seed(1)
+    a = torch.randn(512, 512, device="cuda").to(torch.float8_e4m3fn)
+    bt = torch.randn(768, 512, device="cuda").to(torch.float8_e4m3fn)
+    bias = torch.randn(768, device="cuda")
+    two = native.gemm_tc(a, bt, 5, 10, k_slice=0, operand_mode=native.OPERAND_E4M3, bias=bias, variant=native.GEMM_2CTA)
+    ref = (a.float() @ bt.float().t()).half().float() + bias
+    assert (two - ref).abs().max() <= 2e-3 * ref.abs().max()
+    with pytest.raises(RuntimeError):
+        native.gemm_tc(a, bt, 6, 9, operand_mode=native.OPERAND_E4M3, variant=native.GEMM_2CTA)      # not a packed format

@@ -66,13 +66,18 @@ def main():
             a = torch.randn(M, K, device="cuda").to(dt)
             bt = torch.randn(N, K, device="cuda").to(dt)
             out = torch.empty(M, N, device="cuda")
-            for (e, m, kahan, ks) in ((8, 23, False, 0), (5, 10, False, 1024), (5, 10, False, 256), (4, 3, False, 128), (5, 2, True, 256)):
+            for (e, m, kahan, ks) in ((8, 23, False, 0), (5, 10, False, 0), (5, 10, False, 1024), (5, 10, False, 256), (4, 3, False, 128), (5, 2, True, 256)):
                 if ks and ks > K:
                     continue
-                ms = time_ms(lambda: native.gemm_tc(a, bt, e, m, kahan=kahan, k_slice=ks, operand_mode=mode, out=out), iters=5, warm=2, flush=False)
-                tf = 2.0 * M * N * K / ms / 1e9
-                res["gemm_tc"].append({"M": M, "N": N, "K": K, "operands": name, "acc": [e, m], "kahan": kahan, "k_slice": ks or K,
-                                       "ms": round(ms, 4), "TFLOPs": round(tf, 1), "frac_bf16_peak_" + src: round(tf / tflops, 3)})
+                for variant, vname in ((native.GEMM_1CTA, "1cta_128x128"), (native.GEMM_2CTA, "2cta_256x256")):
+                    if variant == native.GEMM_2CTA and (e, m) == (8, 23):
+                        continue
+                    ms = time_ms(lambda: native.gemm_tc(a, bt, e, m, kahan=kahan, k_slice=ks, operand_mode=mode, out=out, variant=variant),
+                                 iters=5, warm=2, flush=False)
+                    tf = 2.0 * M * N * K / ms / 1e9
+                    res["gemm_tc"].append({"M": M, "N": N, "K": K, "operands": name, "acc": [e, m], "kahan": kahan, "k_slice": ks or K,
+                                           "variant": vname, "ms": round(ms, 4), "TFLOPs": round(tf, 1),
+                                           "frac_bf16_peak_" + src: round(tf / tflops, 3)})
             if name == "bf16":
                 ms = time_ms(lambda: torch.matmul(a, bt.t()), iters=5, warm=2, flush=False)
                 res["gemm_tc"].append({"M": M, "N": N, "K": K, "operands": "bf16", "cublas_ms": round(ms, 4),
