@@ -32,6 +32,8 @@ CUDA_SOURCES = [
     "cuda/gemm_exact_sm100.cu",
     "cuda/gemm_tcgen05_sm100a.cu",
     "cuda/gemm_tcgen05_2cta_sm100a.cu",
+    "cuda/gemm_tcgen05_mx_sm100a.cu",
+    "cuda/mx_quantize_sm100.cu",
     "cuda/allreduce_fused_sm100a.cu",
 ]
 CPP_SOURCES = [

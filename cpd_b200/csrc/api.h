@@ -93,6 +93,11 @@ void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunk
 // packed 16-bit accumulators; formats (5,10), (8,7), (4,3), (5,2) only)
 int gemm_tc_cuda(const void* A, const void* B, float* C, int M, int N, int K, int e, int m,
                  bool kahan, int k_slice, int operand_mode, const float* bias, int variant, cudaStream_t st);
+// MXFP8 operand staging: fp32 [R,K] -> fp8 codes [R,Kp] + UE8M0 per-32 block scales in the tcgen05 scale-factor atom layout
+void mx_quantize_cuda(const float* in, long long ld_in, uint8_t* codes, uint8_t* sf, int R, int K, int Kp, bool e5m2, cudaStream_t st);
+// block-scaled GEMM (tcgen05.mma.kind::mxf8f6f4.block_scale) with per-K-slice accumulator requant
+int gemm_tc_mx_cuda(const uint8_t* codes_a, const uint8_t* sf_a, const uint8_t* codes_b, const uint8_t* sf_b, float* C, int M, int N,
+                    int Kp, int e, int m, bool kahan, int k_slice, bool e5m2, const float* bias, cudaStream_t st);
 int gemm_tc2_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, int e, int m, bool kahan, int k_slice,
                   int operand_mode, const float* bias, cudaStream_t st);
 #endif

@@ -86,6 +86,19 @@ PYBIND11_MODULE(_C, m) {
     return rc;
   });
 
+  m.def("mx_quantize_cuda", [](uptr in, int64_t ld_in, uptr codes, uptr sf, int R, int K, int Kp, bool e5m2, uptr stream) {
+    cpd::mx_quantize_cuda(P<const float>(in), ld_in, P<uint8_t>(codes), P<uint8_t>(sf), R, K, Kp, e5m2, S(stream));
+    check_launch("mx_quantize");
+  });
+  m.def("gemm_tc_mx_cuda", [](uptr ca, uptr sa, uptr cb, uptr sb, uptr C, int M, int N, int Kp, int e, int mb, bool kahan, int k_slice,
+                              bool e5m2, uptr bias, uptr stream) {
+    check_fmt(e, mb);
+    int rc = cpd::gemm_tc_mx_cuda(P<const uint8_t>(ca), P<const uint8_t>(sa), P<const uint8_t>(cb), P<const uint8_t>(sb), P<float>(C), M,
+                                  N, Kp, e, mb, kahan, k_slice, e5m2, P<const float>(bias), S(stream));
+    check_launch("gemm_tc_mx");
+    return rc;
+  });
+
   // --------------------------------------------------------- multi-tensor arenas --
   m.def("aps_fold_cpu", [](std::vector<uptr> srcs, uptr out, uptr seg_off, int T, int e, int mb, bool use_aps, bool kahan,
                            double world_mult, uptr shifts_out) {

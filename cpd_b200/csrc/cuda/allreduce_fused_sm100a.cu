@@ -190,19 +190,38 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
 
   // ---------------- phase A: per-tensor amax, exponent exchange ---------------------
   if (p.use_aps) {
-    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
-      const Chunk ck = p.chunks[c];
+    // contiguous chunk range per CTA: consecutive chunks mostly belong to the same tensor, so the
+    // per-thread maxima are carried across chunks and the block reduction + atomic happen only
+    // when the tensor changes (large tensors: ~1 reduction per CTA instead of 1 per chunk)
+    {
+      const int per = (p.n_chunks + gridDim.x - 1) / gridDim.x;
+      const int c0 = blockIdx.x * per, c1 = min(p.n_chunks, c0 + per);
       unsigned m = 0u;
-      for (int g = threadIdx.x; g < (ck.len >> 4); g += kArThreads) {
-        const uint4* q = reinterpret_cast<const uint4*>(p.grad + ck.start + 16 * g);
+      int cur_tensor = -1;
+      for (int c = c0; c < c1; ++c) {
+        const Chunk ck = p.chunks[c];
+        if (ck.tensor != cur_tensor) {
+          if (cur_tensor >= 0) {
+            m = block_max_u32(m, red);
+            if (threadIdx.x == 0 && m) atomicMax(&amax[cur_tensor], m);
+          }
+          cur_tensor = ck.tensor;
+          m = 0u;
+        }
+        for (int g = threadIdx.x; g < (ck.len >> 4); g += kArThreads) {
+          const uint4* q = reinterpret_cast<const uint4*>(p.grad + ck.start + 16 * g);
+          uint4 x[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 x = q[i];
-          m = max(max(m, x.x & 0x7FFFFFFFu), max(x.y & 0x7FFFFFFFu, max(x.z & 0x7FFFFFFFu, x.w & 0x7FFFFFFFu)));
+          for (int i = 0; i < 4; ++i) x[i] = q[i];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            m = max(max(m, x[i].x & 0x7FFFFFFFu), max(x[i].y & 0x7FFFFFFFu, max(x[i].z & 0x7FFFFFFFu, x[i].w & 0x7FFFFFFFu)));
         }
       }
-      m = block_max_u32(m, red);
-      if (threadIdx.x == 0 && m) atomicMax(&amax[ck.tensor], m);
+      if (cur_tensor >= 0) {
+        m = block_max_u32(m, red);
+        if (threadIdx.x == 0 && m) atomicMax(&amax[cur_tensor], m);
+      }
     }
     grid_barrier(bar);
     if (blockIdx.x == 0) {

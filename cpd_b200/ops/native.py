@@ -171,6 +171,51 @@ def gemm_tc(a: torch.Tensor, bt: torch.Tensor, exp: int, man: int, kahan: bool =
     return out
 
 
+def mx_quantize(x: torch.Tensor, e5m2: bool = False):
+    """fp32 [R, K] (row stride arbitrary) -> (codes uint8 [R, Kp], block scales uint8 atoms): MXFP8 with one
+    UE8M0 power-of-two scale per 32 consecutive K-elements, laid out for tcgen05 (see mx_quantize_sm100.cu)."""
+    _f32(x, "x")
+    if not x.is_cuda or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("mx_quantize: 2-D CUDA tensor with unit inner stride expected")
+    R, K = x.shape
+    Kp = (K + 127) // 128 * 128
+    codes = torch.empty(R, Kp, dtype=torch.uint8, device=x.device)
+    sf = torch.zeros(((R + 127) // 128) * (Kp // 128) * 512, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _C.mx_quantize_cuda(x.data_ptr(), x.stride(0), codes.data_ptr(), sf.data_ptr(), R, K, Kp, bool(e5m2), _stream(x))
+    return codes, sf
+
+
+def mx_dequantize(codes: torch.Tensor, sf: torch.Tensor, K: int, e5m2: bool = False) -> torch.Tensor:
+    """Host-side model of what the tensor core sees: codes * 2^(scale-127), for tests."""
+    R, Kp = codes.shape
+    vals = codes.view(torch.float8_e5m2 if e5m2 else torch.float8_e4m3fn).float()
+    r = torch.arange(R, device=codes.device)
+    kb = torch.arange(Kp // 32, device=codes.device)
+    atom = (r[:, None] // 128) * (Kp // 128) + (kb[None, :] // 4)
+    off = atom * 512 + (r[:, None] % 32) * 16 + ((r[:, None] // 32) % 4) * 4 + (kb[None, :] % 4)
+    scale = torch.exp2(sf[off].float() - 127.0)
+    return (vals.view(R, Kp // 32, 32) * scale[:, :, None]).view(R, Kp)[:, :K]
+
+
+def gemm_tc_mx(a_codes, a_sf, bt_codes, bt_sf, exp: int, man: int, kahan: bool = False, k_slice: int = 128, e5m2: bool = False,
+               bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Block-scaled fp8 GEMM: C[M,N] = (A codes x A scales) @ (Bt codes x Bt scales)^T on tcgen05
+    kind::mxf8f6f4.block_scale, accumulator re-quantised to (exp, man) after every K-slice."""
+    _check_fmt(exp, man)
+    M, Kp = a_codes.shape
+    N = bt_codes.shape[0]
+    if bt_codes.shape[1] != Kp or Kp % 128:
+        raise ValueError("gemm_tc_mx: operands must share a K padded to a multiple of 128")
+    out = torch.empty(M, N, dtype=torch.float32, device=a_codes.device)
+    with torch.cuda.device(a_codes.device):
+        rc = _C.gemm_tc_mx_cuda(a_codes.data_ptr(), a_sf.data_ptr(), bt_codes.data_ptr(), bt_sf.data_ptr(), out.data_ptr(), M, N, Kp,
+                                int(exp), int(man), bool(kahan), int(k_slice), bool(e5m2), _ptr(bias), _stream(a_codes))
+    if rc != 0:
+        raise RuntimeError(f"gemm_tc_mx: kernel rejected the problem (code {rc})")
+    return out
+
+
 # --------------------------------------------------------- multi-tensor arenas --
 def aps_fold(srcs: Sequence[torch.Tensor], out: torch.Tensor, seg_off: torch.Tensor, exp: int, man: int,
              use_aps: bool, kahan: bool, world_mult: float, chunks: Optional[torch.Tensor] = None,

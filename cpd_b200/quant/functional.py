@@ -96,6 +96,8 @@ def quant_gemm(a: torch.Tensor, b: torch.Tensor, man: int = 23, exp: int = 8, mo
         man<=7, tf32 otherwise.  Large problems in the 16-bit-representable formats run on
         CTA pairs (thread-block clusters, cta_group::2) with packed 16-bit accumulators.
     mode="auto":  exact on CPU and for small problems, tile otherwise.
+    ``operands``: "bf16" | "tf32" | "e4m3" | "e5m2" | "mxe4m3" | "mxe5m2" (block-scaled fp8: one
+    UE8M0 scale per 32 K-elements, tcgen05 kind::mxf8f6f4.block_scale); default by format.
     ``kahan`` defaults to True for exact (as the reference) and False for tile.
     """
     assert len(a.shape) == 2
@@ -115,6 +117,11 @@ def quant_gemm(a: torch.Tensor, b: torch.Tensor, man: int = 23, exp: int = 8, mo
         raise ValueError(f"unknown gemm mode {mode!r}")
     if not a.is_cuda:
         raise NotImplementedError("mode='tile' needs a CUDA device (use ops.native.gemm_tile_cpu for the CPU model)")
+    if operands in ("mxe4m3", "mxe5m2"):       # block-scaled fp8 operands (one power-of-two scale per 32 K-elements)
+        e5 = operands == "mxe5m2"
+        ac, asf = native.mx_quantize(a.contiguous(), e5)
+        bc, bsf = native.mx_quantize(b.t().contiguous(), e5)
+        return native.gemm_tc_mx(ac, asf, bc, bsf, exp, man, bool(kahan) if kahan is not None else False, k_slice, e5, bias)
     om = _OPERAND_NAME[operands] if operands else _operand_mode(exp, man)
     dt = _OPERAND_DTYPE[om]
     a_op = a.to(dt).contiguous()
