@@ -58,3 +58,24 @@ class PinnedBatchStream:
         b = self.batches[self.i % len(self.batches)]
         self.i += 1
         return b
+
+
+class Batches:
+    """DataLoader wrapper of the DavidNet recipe (reference: example/DavidNet/utils.py:152-178): yields
+    {'input', 'target'} dicts already on the device; uses a DistributedSampler when ``distributed``."""
+
+    def __init__(self, dataset, batch_size, shuffle, num_workers=0, drop_last=False, distributed=False, device=None):
+        self.dataset = dataset
+        self.device = device or (torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu"))
+        sampler = None
+        if distributed:
+            from torch.utils.data.distributed import DistributedSampler as TorchDS
+            sampler = TorchDS(dataset, shuffle=shuffle)
+        self.loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, num_workers=num_workers, pin_memory=torch.cuda.is_available(),
+                                                  shuffle=(shuffle and sampler is None), drop_last=drop_last, sampler=sampler)
+
+    def __iter__(self):
+        return ({"input": x.to(self.device, non_blocking=True), "target": y.to(self.device, non_blocking=True).long()} for (x, y) in self.loader)
+
+    def __len__(self):
+        return len(self.loader)

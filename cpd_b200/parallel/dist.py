@@ -152,3 +152,11 @@ def is_distributed() -> bool:
 def shutdown() -> None:
     if dist.is_available() and dist.is_initialized():
         dist.destroy_process_group()
+
+
+def simple_group_split(world_size: int, rank: int, num_groups: int):
+    """Split the world into ``num_groups`` contiguous process groups and return the one containing
+    ``rank`` (reference: train_util.py:11-18, a helper the reference defines but never calls)."""
+    size = world_size // num_groups
+    groups = [dist.new_group(list(range(i * size, (i + 1) * size))) for i in range(num_groups)]
+    return groups[rank // size]

@@ -18,6 +18,7 @@ reduction overlaps the rest of backward (``overlap=True``).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -32,6 +33,8 @@ _ALGO = {"auto": native.ALGO_AUTO, "oneshot": native.ALGO_ONESHOT, "twoshot": na
 
 # packed bytes per bucket below which the one-shot variant (1 exchange fewer, W x the
 # fold work and (W-1)/1 x the NVLink reads) beats two-shot; tuned on 8xB200
+_FAULT_DELAY_RANK = int(os.environ.get("CPD_B200_FAULT_DELAY_RANK", "-1"))
+_FAULT_DELAY_CYCLES = float(os.environ.get("CPD_B200_FAULT_DELAY_CYCLES", "2e8"))
 ONESHOT_MAX_BYTES = 256 * 1024
 MAX_TENSORS_PER_BUCKET = 1024
 
@@ -116,6 +119,9 @@ class GradReducer:
     # ------------------------------------------------------------------- reduce --
     def reduce_bucket(self, i: int, grad_flat: Optional[torch.Tensor] = None) -> None:
         cfg, b = self.cfg, self.buckets[i]
+        if _FAULT_DELAY_RANK == self.rank and self.is_cuda:
+            # fault injection for tests: this rank reaches the collective late (bounded-spin paths)
+            torch.cuda._sleep(int(_FAULT_DELAY_CYCLES))
         g = self._bucket_view(self.arena.grad_flat if grad_flat is None else grad_flat, b)
         e, m = cfg.grad_exp, cfg.grad_man
         if self.mode == "local":

@@ -24,12 +24,17 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
+import os
+
 from ..config import PrecisionConfig
 from ..optim import FusedSGD
 from ..parallel.api import broadcast_params
 from ..parallel.arena import ModelArena
 from ..parallel.emulate import EmulateNode
 from ..parallel.reducer import GradReducer
+
+
+_NVTX = os.environ.get("CPD_B200_NVTX", "0") == "1"      # NVTX ranges around fwd/bwd, gradient sync, optimizer
 
 
 class TrainEngine:
@@ -81,11 +86,14 @@ class TrainEngine:
         return F.cross_entropy(logits, target, reduction=red)
 
     def _step_body(self) -> None:
+        nvtx = torch.cuda.nvtx if (self.is_cuda and _NVTX) else None
         self.loss_dev.zero_()
         denom = float(self.world * self.E)
         overlap = self.cfg.overlap and self.E == 1
         for k in range(self.E):
             self.emulate.begin_micro(k)
+            if nvtx:
+                nvtx.range_push(f"fwd_bwd[{k}]")
             xin = self.x[k]
             if self.channels_last:
                 xin = xin.contiguous(memory_format=torch.channels_last)
@@ -95,9 +103,18 @@ class TrainEngine:
                 self.reducer.arm()
             (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
             self.loss_dev += loss.detach()
+            if nvtx:
+                nvtx.range_pop()
+        if nvtx:
+            nvtx.range_push("grad_sync")
         self.emulate.fold()
         self.reducer.reduce()
+        if nvtx:
+            nvtx.range_pop()
+            nvtx.range_push("optimizer")
         self.optimizer.step()
+        if nvtx:
+            nvtx.range_pop()
 
     def _capture(self) -> None:
         self.graph = torch.cuda.CUDAGraph()

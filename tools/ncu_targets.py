@@ -22,6 +22,12 @@ if which in ("all", "gemm_tc"):
     a8, b8 = a.to(torch.float8_e4m3fn), bt.to(torch.float8_e4m3fn)
     for _ in range(3):
         native.gemm_tc(a8, b8, 4, 3, kahan=False, k_slice=512, operand_mode=native.OPERAND_E4M3)
+if which in ("gemm_tc2",):
+    M = N = K = 8192
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    bt = torch.randn(N, K, device="cuda").bfloat16()
+    for _ in range(3):
+        native.gemm_tc(a, bt, 5, 10, kahan=False, k_slice=256, operand_mode=native.OPERAND_BF16, variant=native.GEMM_2CTA)
 if which in ("all", "fold", "lars"):
     numels = [p.numel() for p in create_model("resnet18_cifar").parameters()]
     layout = ArenaLayout(numels)
