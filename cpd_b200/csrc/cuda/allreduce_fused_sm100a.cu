@@ -176,6 +176,15 @@ __device__ __forceinline__ void wait_peers(const ArParams& p, int phase, unsigne
   __syncthreads();
 }
 
+// phase timestamps (ns, %globaltimer) of CTA 0 for attribution: ws tail, 8 x u64 after the amax buffers
+__device__ __forceinline__ void stamp(const ArParams& p, int i) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    reinterpret_cast<unsigned long long*>(p.ws + 4 + 2 * p.max_tensors)[i] = t;
+  }
+}
+
 template <class F, int WIRE, bool KAHAN>
 __global__ void __launch_bounds__(kArThreads, 2)
 allreduce_fused_kernel(const ArParams p, const F fmt) {
@@ -188,6 +197,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
   unsigned* amax = p.ws + 4 + par * p.max_tensors;
   unsigned char* my_data = p.data[rank] + par * p.cap_bytes;
 
+  stamp(p, 0);
   // ---------------- phase A: per-tensor amax, exponent exchange ---------------------
   if (p.use_aps) {
     // contiguous chunk range per CTA: consecutive chunks mostly belong to the same tensor, so the
@@ -224,6 +234,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
       }
     }
     grid_barrier(bar);
+    stamp(p, 1);
     if (blockIdx.x == 0) {
       float* mb = p.mailbox[rank] + par * p.max_tensors;
       unsigned* amax_next = p.ws + 4 + (par ^ 1u) * p.max_tensors;
@@ -251,6 +262,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
     __syncthreads();
   }
 
+  stamp(p, 2);
   // ---------------- phase B: scale, cast, pack into the local wire buffer -----------
   for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
     const Chunk ck = p.chunks[c];
@@ -270,8 +282,10 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
     }
   }
   grid_barrier(bar);
+  stamp(p, 3);
   signal_peers(p, 1, epoch);
   wait_peers(p, 1, epoch);
+  stamp(p, 4);
 
   // ---------------- phase C: rank-ordered quantised fold over peer memory ----------
   const bool two_shot = p.algo != ALGO_ONESHOT;
@@ -329,10 +343,12 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
   }
 
   // ---------------- phase D (two-shot): adopt the slices reduced by the peers ---------
+  stamp(p, 5);
   if (two_shot) {
     grid_barrier(bar);
     signal_peers(p, 2, epoch);
     wait_peers(p, 2, epoch);
+    stamp(p, 6);
     const unsigned char* my_gather = p.gather[rank] + par * p.cap_bytes;
     for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
       if (c % W == rank) continue;
@@ -352,6 +368,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
     }
   }
 
+  stamp(p, 7);
   if (blockIdx.x == 0 && threadIdx.x == 0) p.ws[2] = epoch;
 }
 

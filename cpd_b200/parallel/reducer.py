@@ -88,7 +88,7 @@ class GradReducer:
         self.symm = None
         self._gather_buf = None
         if self.is_cuda:
-            self.local_ws = torch.zeros(4 + 2 * MAX_TENSORS_PER_BUCKET, dtype=torch.int32, device=self.device)
+            self.local_ws = torch.zeros(4 + 2 * MAX_TENSORS_PER_BUCKET + 32, dtype=torch.int32, device=self.device)
         if self.mode == "fused":
             from .symm import SymmetricWorkspace
             self.symm = SymmetricWorkspace(self.max_numel * (self.wire // 8), MAX_TENSORS_PER_BUCKET, group=group)
@@ -217,6 +217,16 @@ class GradReducer:
         if st & 0x80000000:
             phase, peer = (st >> 8) & 0xFF, st & 0xFF
             raise RuntimeError(f"cpd_b200: fused all-reduce timed out in phase {phase} waiting for rank {peer}")
+
+    def phase_times_us(self) -> dict:
+        """Per-phase durations (us) of the LAST fused launch, from the %globaltimer stamps CTA 0 leaves in the
+        workspace: amax, exponent exchange, pack, data barrier, fold, gather barrier (two-shot), unpack."""
+        if self.local_ws is None or self.mode != "fused":
+            return {}
+        t = self.local_ws[4 + 2 * MAX_TENSORS_PER_BUCKET:4 + 2 * MAX_TENSORS_PER_BUCKET + 16].cpu().view(torch.int64).tolist()
+        d = lambda a, b: round((t[b] - t[a]) / 1e3, 2) if t[a] and t[b] and t[b] >= t[a] else None  # noqa: E731
+        return {"A_amax+gridbar": d(0, 1), "exp_exchange": d(1, 2), "B_pack+gridbar": d(2, 3), "data_flags": d(3, 4), "C_fold": d(4, 5),
+                "gather_gridbar+flags": d(5, 6), "D_unpack": d(6, 7) if t[6] else None, "total": d(0, 7)}
 
     def remove_hooks(self) -> None:
         for h in self._hooks:

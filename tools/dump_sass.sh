@@ -19,12 +19,15 @@ pick = {
  'aps_fold_local_kernel': r'aps_fold_local_kernel.*FmtTILi4ELi3EEELb0',
  'lars_kernel': r'lars_kernel',
  'gemm_exact_kernel': r'gemm_exact_kernel.*FmtTILi4ELi3EEELb1',
- 'gemm_tcgen05_kernel_bf16': r'gemm_tcgen05_kernelILi0ENS_4FmtTILi5ELi10EEELb0',
- 'gemm_tcgen05_kernel_fp8': r'gemm_tcgen05_kernelILi2ENS_4FmtTILi4ELi3EEELb0',
+ 'gemm_tcgen05_kernel_bf16': r'gemm_tcgen05_kernelILi0ENS_8FmtHwF16ELb0',
+ 'gemm_tcgen05_kernel_fp8': r'gemm_tcgen05_kernelILi2ENS_9FmtHwE4M3ELb0',
+ 'gemm_tcgen05_2cta_kernel_bf16_f16acc': r'gemm_tcgen05_2cta_kernelILi0ENS_3tc26AccF16ELb0',
+ 'gemm_tcgen05_mx_kernel': r'gemm_tcgen05_mx_kernelINS_8FmtHwF16ELb0',
+ 'mx_quantize_kernel': r'mx_quantize_kernelILb0',
  'allreduce_fused_kernel_e4m3': r'allreduce_fused_kernel.*FmtTILi4ELi3EEELi8ELb0',
  'allreduce_fused_kernel_e5m2_kahan': r'allreduce_fused_kernel.*FmtTILi5ELi2EEELi8ELb1',
 }
-interesting = re.compile(r'\b(UTC[A-Z]*MMA[\w.]*|UTCBAR[\w.]*|UTCATOMSWS[\w.]*|LDTM[\w.]*|STTM[\w.]*|UTMALDG[\w.]*|UBLKCP[\w.]*|SYNCS[\w.]*|LDG\.E[\w.]*|STG\.E[\w.]*|LD\.E[\w.]*|ST\.E[\w.]*|MULTIMEM[\w.]*|LDGMC[\w.]*|STGMC[\w.]*|REDG?[\w.]*|ATOM[GS]?[\w.]*|MEMBAR[\w.]*|FENCE[\w.]*|CCTL[\w.]*|NANOSLEEP[\w.]*|BAR\.[\w.]*|LOP3[\w.]*|HMMA[\w.]*)')
+interesting = re.compile(r'\b(UTC[A-Z]*MMA[\w.]*|UTCBAR[\w.]*|UTCCP[\w.]*|F2FP[\w.]*|F2F\.[\w.]*|UCGABAR[\w.]*|UTCATOMSWS[\w.]*|LDTM[\w.]*|STTM[\w.]*|UTMALDG[\w.]*|UBLKCP[\w.]*|SYNCS[\w.]*|LDG\.E[\w.]*|STG\.E[\w.]*|LD\.E[\w.]*|ST\.E[\w.]*|MULTIMEM[\w.]*|LDGMC[\w.]*|STGMC[\w.]*|REDG?[\w.]*|ATOM[GS]?[\w.]*|MEMBAR[\w.]*|FENCE[\w.]*|CCTL[\w.]*|NANOSLEEP[\w.]*|BAR\.[\w.]*|LOP3[\w.]*|HMMA[\w.]*)')
 lines = ["# SASS evidence (cuobjdump -sass of cpd_b200/_C*.so, sm_100a)\n"]
 for name, pat in pick.items():
     f = [x for x in funcs if re.search(pat, x.split('\n', 1)[0])]

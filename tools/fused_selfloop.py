@@ -41,6 +41,7 @@ for name, numels in layouts.items():
             n = arena.layout.total
             rows.append({"layout": name, "algo": algo, "kahan": kahan, "us": round(ms * 1e3, 2), "elems": n,
                          "local_bytes_per_elem": 13, "frac_of_hbm_" + src: round(13.0 * n / ms / 1e6 / hbm, 3)})
+            rows[-1]["phases_us"] = red.phase_times_us()
             print(json.dumps(rows[-1]), flush=True)
             del red
 dist.destroy_process_group()

@@ -202,6 +202,7 @@ def section_sweep(rank, world, res, max_bytes):
                 continue
             ms = time_calls(red.reduce, iters)
             row[f"fused_{algo}_us"] = round(ms * 1e3, 2)
+            row[f"fused_{algo}_phases_us"] = red.phase_times_us()
             row[f"fused_{algo}_busbw_fp32_GBps"] = round(nbytes / (ms * 1e-3) * 2 * (world - 1) / world / 1e9, 2)
             row[f"fused_{algo}_wire_GBps"] = round((n * red.wire / 8) / (ms * 1e-3) * 2 * (world - 1) / world / 1e9, 2)
             del red
