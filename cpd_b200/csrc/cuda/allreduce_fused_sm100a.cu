@@ -208,8 +208,20 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
       const int c0 = blockIdx.x * per, c1 = min(p.n_chunks, c0 + per);
       unsigned m = 0u;
       int cur_tensor = -1;
-      for (int c = c0; c < c1; ++c) {
+      for (int c = c0; c < c1; c += 2) {
+        const bool has2 = c + 1 < c1;
         const Chunk ck = p.chunks[c];
+        const Chunk ckn = has2 ? p.chunks[c + 1] : ck;
+        // both chunks' vectors are requested before either is reduced
+        uint4 x[4], y[4];
+        const bool a0 = (int)threadIdx.x < (ck.len >> 4), a1 = has2 && (int)threadIdx.x < (ckn.len >> 4);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        const uint4* q0 = reinterpret_cast<const uint4*>(p.grad + ck.start + 16 * threadIdx.x);
+        const uint4* q1 = reinterpret_cast<const uint4*>(p.grad + ckn.start + 16 * threadIdx.x);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = a0 ? q0[i] : z;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = a1 ? q1[i] : z;
         if (ck.tensor != cur_tensor) {
           if (cur_tensor >= 0) {
             m = block_max_u32(m, red);
@@ -218,14 +230,19 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
           cur_tensor = ck.tensor;
           m = 0u;
         }
-        for (int g = threadIdx.x; g < (ck.len >> 4); g += kArThreads) {
-          const uint4* q = reinterpret_cast<const uint4*>(p.grad + ck.start + 16 * g);
-          uint4 x[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) x[i] = q[i];
+        for (int i = 0; i < 4; ++i)
+          m = max(max(m, x[i].x & 0x7FFFFFFFu), max(x[i].y & 0x7FFFFFFFu, max(x[i].z & 0x7FFFFFFFu, x[i].w & 0x7FFFFFFFu)));
+        if (has2) {
+          if (ckn.tensor != cur_tensor) {
+            m = block_max_u32(m, red);
+            if (threadIdx.x == 0 && m) atomicMax(&amax[cur_tensor], m);
+            cur_tensor = ckn.tensor;
+            m = 0u;
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            m = max(max(m, x[i].x & 0x7FFFFFFFu), max(x[i].y & 0x7FFFFFFFu, max(x[i].z & 0x7FFFFFFFu, x[i].w & 0x7FFFFFFFu)));
+            m = max(max(m, y[i].x & 0x7FFFFFFFu), max(y[i].y & 0x7FFFFFFFu, max(y[i].z & 0x7FFFFFFFu, y[i].w & 0x7FFFFFFFu)));
         }
       }
       if (cur_tensor >= 0) {
@@ -264,21 +281,40 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
 
   stamp(p, 2);
   // ---------------- phase B: scale, cast, pack into the local wire buffer -----------
-  for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
-    const Chunk ck = p.chunks[c];
-    const float sc = p.use_aps ? pow2i(s_shift[ck.tensor]) : 1.f;
-    for (int g = threadIdx.x; g < (ck.len >> 4); g += kArThreads) {
-      const long long e0 = ck.start + 16 * g;
-      float x[16];
-      load16(p.grad + e0, x);
+  // two chunks per CTA iteration: 8 x 16 B loads in flight per thread before the first use (the local
+  // passes are latency-bound: bytes in flight / ~1.2 us of loaded HBM latency)
+  for (int c = blockIdx.x; c < p.n_chunks; c += 2 * gridDim.x) {
+    const int c2 = c + gridDim.x;
+    const bool has2 = c2 < p.n_chunks;
+    const Chunk ck0 = p.chunks[c];
+    const Chunk ck1 = has2 ? p.chunks[c2] : ck0;
+    const bool a0 = (int)threadIdx.x < (ck0.len >> 4);
+    const bool a1 = has2 && (int)threadIdx.x < (ck1.len >> 4);
+    const long long e0 = ck0.start + 16 * threadIdx.x, e1 = ck1.start + 16 * threadIdx.x;
+    float x0[16], x1[16];
+    if (a0) load16(p.grad + e0, x0);
+    if (a1) load16(p.grad + e1, x1);
+    if (a0) {
+      const float sc = p.use_aps ? pow2i(s_shift[ck0.tensor]) : 1.f;
       if (p.use_aps) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = fmt.q(x[i] * sc);
+        for (int i = 0; i < 16; ++i) x0[i] = fmt.q(x0[i] * sc);
       } else if (p.prequant) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = fmt.q(x[i]);
+        for (int i = 0; i < 16; ++i) x0[i] = fmt.q(x0[i]);
       }
-      granule_store<WIRE>(my_data, e0, granule_encode<WIRE>(fmt, x), false);
+      granule_store<WIRE>(my_data, e0, granule_encode<WIRE>(fmt, x0), false);
+    }
+    if (a1) {
+      const float sc = p.use_aps ? pow2i(s_shift[ck1.tensor]) : 1.f;
+      if (p.use_aps) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x1[i] = fmt.q(x1[i] * sc);
+      } else if (p.prequant) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x1[i] = fmt.q(x1[i]);
+      }
+      granule_store<WIRE>(my_data, e1, granule_encode<WIRE>(fmt, x1), false);
     }
   }
   grid_barrier(bar);
@@ -350,20 +386,35 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
     wait_peers(p, 2, epoch);
     stamp(p, 6);
     const unsigned char* my_gather = p.gather[rank] + par * p.cap_bytes;
-    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
-      if (c % W == rank) continue;
-      const Chunk ck = p.chunks[c];
-      const float inv = p.use_aps ? pow2i(-s_shift[ck.tensor]) : 1.f;
-      for (int g = threadIdx.x; g < (ck.len >> 4); g += kArThreads) {
-        const long long e0 = ck.start + 16 * g;
-        const Granule<WIRE> in = granule_load_sys<WIRE>(my_gather, e0);
+    for (int c = blockIdx.x; c < p.n_chunks; c += 2 * gridDim.x) {
+      const int c2 = c + gridDim.x;
+      const bool u0 = (c % W) != rank, u1 = c2 < p.n_chunks && (c2 % W) != rank;
+      const Chunk ck0 = p.chunks[c];
+      const Chunk ck1 = u1 ? p.chunks[c2] : ck0;
+      const bool a0 = u0 && (int)threadIdx.x < (ck0.len >> 4), a1 = u1 && (int)threadIdx.x < (ck1.len >> 4);
+      const long long e0 = ck0.start + 16 * threadIdx.x, e1 = ck1.start + 16 * threadIdx.x;
+      Granule<WIRE> in0, in1;
+      if (a0) in0 = granule_load_sys<WIRE>(my_gather, e0);
+      if (a1) in1 = granule_load_sys<WIRE>(my_gather, e1);
+      if (a0) {
+        const float inv = p.use_aps ? pow2i(-s_shift[ck0.tensor]) : 1.f;
         float v[16];
-        granule_decode<WIRE>(fmt, in, v);
+        granule_decode<WIRE>(fmt, in0, v);
         if (p.use_aps) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= inv;
         }
         store16(p.grad + e0, v);
+      }
+      if (a1) {
+        const float inv = p.use_aps ? pow2i(-s_shift[ck1.tensor]) : 1.f;
+        float v[16];
+        granule_decode<WIRE>(fmt, in1, v);
+        if (p.use_aps) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= inv;
+        }
+        store16(p.grad + e1, v);
       }
     }
   }

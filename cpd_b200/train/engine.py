@@ -118,7 +118,8 @@ class TrainEngine:
 
     def _capture(self) -> None:
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: DataLoader pin-memory / worker threads may legally call cudaHostAlloc etc. while we capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self._step_body()
 
     # ------------------------------------------------------------------- public --
