@@ -75,7 +75,7 @@ struct CommBuffers {
   // per-rank device pointers into the symmetric region (index = rank)
   unsigned char* data[16];     // wire buffers   [2][cap_bytes]
   unsigned char* gather[16];   // reduced-slice buffers [2][cap_bytes]
-  float* mailbox[16];          // APS exponents  [2][max_tensors]
+  float* mailbox[16];          // APS exponents  [2 parities][8 source ranks][max_tensors] (pushed by the sources)
   unsigned* flags[16];         // signal pad     [3][16] epoch flags per phase
   unsigned char* mc_gather;    // multicast view of `gather` (nullptr when no NVLS)
   size_t cap_bytes;

@@ -8,8 +8,8 @@
 // >= 2 host syncs per parameter, fp32 on the wire ((W-1)*4 B per element in).
 //
 // This kernel fuses all of it for a whole bucket (many tensors, per-tensor shift):
-//   A  per-tensor max|g|                      -> grid barrier -> exponent to own mailbox,
-//      signal peers; wait peers; shift[t] = bias - max_r ceil(log2(amax_r * W))
+//   A  per-tensor max|g|                      -> grid barrier -> exponents PUSHED into every rank's mailbox,
+//      signal peers; wait peers; shift[t] = bias - max_r ceil(log2(amax_r * W)) from the local mailbox
 //   B  g -> Q(g * 2^shift) -> packed wire code (8/16/32 bit) into own symmetric
 //      buffer                                  -> grid barrier -> signal peers; wait peers
 //   C  one-shot : every rank loads all W peers' codes (128-bit peer loads over
@@ -253,11 +253,14 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
     grid_barrier(bar);
     stamp(p, 1);
     if (blockIdx.x == 0) {
-      float* mb = p.mailbox[rank] + par * p.max_tensors;
+      // PUSH the exponents into every rank's mailbox (slot [parity][source rank][tensor]) so that after the flag
+      // round each rank reads only LOCAL memory: one NVLink round trip less on the critical path
       unsigned* amax_next = p.ws + 4 + (par ^ 1u) * p.max_tensors;
       for (int t = threadIdx.x; t < p.T; t += kArThreads) {
         const unsigned ab = amax[t];
-        mb[t] = ab >= 0x7F800000u ? INFINITY : aps_local_exponent(__uint_as_float(ab), (float)W);
+        const float me = ab >= 0x7F800000u ? INFINITY : aps_local_exponent(__uint_as_float(ab), (float)W);
+        for (int r = 0; r < W; ++r)
+          asm volatile("st.relaxed.sys.global.f32 [%0], %1;" :: "l"(p.mailbox[r] + ((size_t)par * kArMaxW + rank) * p.max_tensors + t), "f"(me) : "memory");
       }
       // the other parity's amax buffer is used by the NEXT launch (possibly a different
       // bucket with more tensors): clear all of it
@@ -269,7 +272,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
     for (int t = threadIdx.x; t < p.T; t += kArThreads) {
       float me = -INFINITY;
       for (int r = 0; r < W; ++r) {
-        const float v = ld_sys_f32(p.mailbox[r] + par * p.max_tensors + t);
+        const float v = ld_sys_f32(p.mailbox[rank] + ((size_t)par * kArMaxW + r) * p.max_tensors + t);
         me = (v != v || me != me) ? NAN : fmaxf(me, v);
       }
       const int sh = aps_shift_from_exponent(me, fmt.exp_bits());

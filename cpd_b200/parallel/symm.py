@@ -45,7 +45,7 @@ class SymmetricWorkspace:
         self.off_data = 0
         self.off_gather = self.off_data + 2 * self.cap_bytes
         self.off_mailbox = self.off_gather + 2 * self.cap_bytes
-        self.off_flags = self.off_mailbox + _round_up(2 * self.max_tensors * 4, _ALIGN)
+        self.off_flags = self.off_mailbox + _round_up(2 * 8 * self.max_tensors * 4, _ALIGN)      # [parity][source rank][tensor]
         self.total = self.off_flags + _round_up(FLAG_WORDS * 4, _ALIGN)
         self.backend = None
         self.log: List[str] = []

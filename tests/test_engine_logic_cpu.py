@@ -1,0 +1,65 @@
+"""Host-side planning logic: bucket ranges, wire selection, algorithm choice, arena views."""
+import pytest
+import torch
+
+from cpd_b200 import PrecisionConfig
+from cpd_b200.parallel import GradReducer, ModelArena
+from cpd_b200.parallel.arena import ArenaLayout, _is_dense
+
+
+def _net():
+    return torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.Flatten(), torch.nn.Linear(8 * 36, 20), torch.nn.Linear(20, 4))
+
+
+def test_layout_alignment_and_chunk_table():
+    lay = ArenaLayout([10, 4096, 4097, 1])
+    assert lay.offsets == [0, 16, 16 + 4096, 16 + 4096 + 4112, 16 + 4096 + 4112 + 16]
+    tab = lay.table("cpu")
+    assert tab.n_chunks == 1 + 1 + 2 + 1 and tab.tchunk_off.tolist() == [0, 1, 2, 4, 5]
+    sub = lay.table("cpu", 1, 3)
+    assert sub.base == 16 and sub.seg_off.tolist() == [0, 4096, 4096 + 4112] and sub.T == 2
+
+
+def test_arena_views_share_storage_and_keep_memory_format():
+    m = _net().to(memory_format=torch.channels_last)
+    w = m[0].weight.data.clone()
+    arena = ModelArena(list(m.parameters()))
+    assert torch.equal(m[0].weight.data, w) and m[0].weight.stride() == w.stride()
+    assert m[0].weight.data_ptr() == arena.model_flat.data_ptr()
+    m(torch.randn(2, 3, 8, 8)).sum().backward()
+    assert m[0].weight.grad.data_ptr() == arena.grad_flat.data_ptr()            # autograd accumulated into the arena
+    assert float(arena.grad_flat.abs().sum()) > 0
+    assert _is_dense(m[0].weight) and not _is_dense(torch.empty(4, 4)[:, ::2])
+
+
+def test_bucket_ranges_cover_all_tensors_in_reverse_order():
+    arena = ModelArena(list(_net().parameters()))
+    T = arena.layout.T
+    assert arena.bucket_ranges(0) == [(0, T)]
+    r = arena.bucket_ranges(2000)
+    assert r[0][1] == T and r[-1][0] == 0 and all(a < b for a, b in r)
+    assert sorted(t for a, b in r for t in range(a, b)) == list(range(T))
+
+
+def test_reducer_wire_and_mode_selection():
+    arena = ModelArena(list(_net().parameters()))
+    assert GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True)).wire == 8
+    assert GradReducer(arena, PrecisionConfig(grad_exp=5, grad_man=10, use_aps=True)).wire == 16
+    assert GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=False)).wire == 32          # raw fp32 travels
+    assert GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=False, prequantize=True)).wire == 8
+    assert GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, wire="16")).wire == 16
+    with pytest.raises(ValueError):
+        GradReducer(arena, PrecisionConfig(grad_exp=5, grad_man=10, use_aps=True, wire="8"))
+    r = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, bucket_mb=0.001))
+    assert r.mode == "local" and len(r.buckets) > 1
+    for p in arena.params:
+        p.grad.normal_()
+    before = arena.grad_flat.clone()
+    r.reduce()                                             # multi-bucket local path == single bucket
+    one = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True))
+    arena.grad_flat.copy_(before)
+    one.reduce()
+    after_one = arena.grad_flat.clone()
+    arena.grad_flat.copy_(before)
+    r.reduce()
+    assert torch.equal(arena.grad_flat, after_one)

@@ -150,3 +150,20 @@ def test_emulate_node_equals_multi_rank_fold():
     native.aps_fold(micro, want, arena.layout.table("cpu").seg_off, 4, 3, True, False, 4.0)
     assert torch.equal(arena.grad_flat, want)
     assert net[0].weight.grad.data_ptr() == arena.grad_views[0].data_ptr()
+
+
+def test_aps_optimizer_hook_runner_interface():
+    from types import SimpleNamespace
+    from cpd_b200.parallel import APSOptimizerHook
+    torch.manual_seed(0)
+    model = torch.nn.Linear(6, 3)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    hook = APSOptimizerHook(grad_exp=5, grad_man=2, use_APS=True, grad_clip={"max_norm": 1.0})
+    x, y = torch.randn(8, 6), torch.randn(8, 3)
+    w0 = model.weight.detach().clone()
+    runner = SimpleNamespace(model=model, optimizer=opt, outputs={"loss": torch.nn.functional.mse_loss(model(x), y)})
+    hook.after_train_iter(runner)
+    assert not torch.equal(model.weight.detach(), w0)
+    from cpd_b200 import float_quantize
+    g = model.weight.grad
+    assert torch.isfinite(g).all()
