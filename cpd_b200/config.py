@@ -19,7 +19,7 @@ class PrecisionConfig:
     use_kahan: bool = False
     emulate_node: int = 1
     rounding: str = "reference"      # "reference" (bit-exact with CPD) | "ieee"
-    algo: str = "auto"               # auto | oneshot | twoshot | nvls | nccl
+    algo: str = "auto"               # auto | oneshot | twoshot | nvls | raw (single-round, small buckets) | nccl
     wire: str = "auto"               # auto | 8 | 16 | 32   (bits per element on NVLink)
     prequantize: bool = False        # without APS: cast before packing (enables a narrow wire; not reference-exact)
     bucket_mb: float = 0.0           # 0 = one bucket (whole model in one launch)
@@ -31,7 +31,7 @@ class PrecisionConfig:
             raise ValueError(f"unsupported format (exp={self.grad_exp}, man={self.grad_man}); exp<=8, man<=23")
         if self.emulate_node < 1:
             raise ValueError("emulate_node must be >= 1")
-        if self.algo not in ("auto", "oneshot", "twoshot", "nvls", "nccl"):
+        if self.algo not in ("auto", "oneshot", "twoshot", "nvls", "raw", "nccl"):
             raise ValueError(f"unknown algo {self.algo!r}")
         self.wire = str(self.wire)
         if self.wire not in ("auto", "8", "16", "32"):
@@ -62,7 +62,7 @@ def add_precision_args(p: argparse.ArgumentParser, grad_exp: int = 5, grad_man: 
     p.add_argument("--use_lars", "--use-lars", dest="use_lars", action="store_true")
     p.add_argument("--emulate_node", "--emulate-node", dest="emulate_node", type=int, default=1)
     p.add_argument("--rounding", choices=["reference", "ieee"], default="reference")
-    p.add_argument("--algo", choices=["auto", "oneshot", "twoshot", "nvls", "nccl"], default="auto")
+    p.add_argument("--algo", choices=["auto", "oneshot", "twoshot", "nvls", "raw", "nccl"], default="auto")
     p.add_argument("--wire", choices=["auto", "8", "16", "32"], default="auto")
     p.add_argument("--bucket_mb", "--bucket-mb", dest="bucket_mb", type=float, default=0.0)
     p.add_argument("--overlap", action="store_true")

@@ -81,7 +81,7 @@ struct CommBuffers {
   size_t cap_bytes;
   int max_tensors;
 };
-enum AllreduceAlgo : int { ALGO_AUTO = 0, ALGO_ONESHOT = 1, ALGO_TWOSHOT = 2, ALGO_NVLS = 3 };
+enum AllreduceAlgo : int { ALGO_AUTO = 0, ALGO_ONESHOT = 1, ALGO_TWOSHOT = 2, ALGO_NVLS = 3, ALGO_ONESHOT_RAW = 4 };
 void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunks, int n_chunks,
                           int T, int e, int m, bool use_aps, bool kahan, int algo, bool prequant, int wire,
                           unsigned* local_ws /*barrier[2], epoch, status, amax[2][T]*/, int* shifts_out,

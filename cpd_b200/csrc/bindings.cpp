@@ -195,7 +195,8 @@ PYBIND11_MODULE(_C, m) {
     if (T > 1024) throw std::invalid_argument("at most 1024 tensors per bucket");
     if (T > b.cb.max_tensors) throw std::invalid_argument("bucket has more tensors than the mailbox holds");
     if (wire != 8 && wire != 16 && wire != 32) throw std::invalid_argument("wire must be 8, 16 or 32");
-    if ((size_t)numel * (size_t)(wire / 8) > b.cb.cap_bytes) throw std::invalid_argument("bucket larger than the symmetric wire buffer");
+    if ((size_t)numel * (size_t)(algo == cpd::ALGO_ONESHOT_RAW ? 4 : wire / 8) > b.cb.cap_bytes)
+      throw std::invalid_argument("bucket larger than the symmetric wire buffer");
     cpd::allreduce_fused_cuda(b.cb, P<float>(grad), P<const cpd::Chunk>(chunks), n_chunks, T, e, mb, use_aps, kahan, algo, prequant,
                               wire, P<unsigned>(local_ws), P<int>(shifts_out), max_ctas, timeout_cycles, S(stream));
     check_launch("allreduce_fused");

@@ -198,6 +198,88 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
   unsigned char* my_data = p.data[rank] + par * p.cap_bytes;
 
   stamp(p, 0);
+  // ---------------- single-round variant for small buckets (ALGO_ONESHOT_RAW) ---------------------------
+  // Latency-bound messages: ONE flag round instead of two.  Each rank publishes its RAW fp32 gradients plus
+  // its per-tensor exponents; after the single barrier every rank knows the global shift and applies
+  // Q(g_r * 2^shift) to each peer's values on the fly while folding in rank order — the same casts in the
+  // same order as the packed variants, hence bit-identical, at 4 B/element on the wire (fine below ~256 KB).
+  if (p.algo == ALGO_ONESHOT_RAW) {
+    float* my_raw = reinterpret_cast<float*>(my_data);
+    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
+      const Chunk ck = p.chunks[c];
+      unsigned m = 0u;
+      for (int g = threadIdx.x; g < (ck.len >> 4); g += kArThreads) {
+        const uint4* q = reinterpret_cast<const uint4*>(p.grad + ck.start + 16 * g);
+        uint4* d = reinterpret_cast<uint4*>(my_raw + ck.start + 16 * g);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 x = q[i];
+          d[i] = x;
+          m = max(max(m, x.x & 0x7FFFFFFFu), max(x.y & 0x7FFFFFFFu, max(x.z & 0x7FFFFFFFu, x.w & 0x7FFFFFFFu)));
+        }
+      }
+      m = block_max_u32(m, red);
+      if (threadIdx.x == 0 && m) atomicMax(&amax[ck.tensor], m);
+    }
+    grid_barrier(bar);
+    stamp(p, 1);
+    if (blockIdx.x == 0) {
+      unsigned* amax_next = p.ws + 4 + (par ^ 1u) * p.max_tensors;
+      for (int t = threadIdx.x; t < p.T; t += kArThreads) {
+        const unsigned ab = amax[t];
+        const float me = ab >= 0x7F800000u ? INFINITY : aps_local_exponent(__uint_as_float(ab), (float)W);
+        for (int r = 0; r < W; ++r)
+          asm volatile("st.relaxed.sys.global.f32 [%0], %1;" :: "l"(p.mailbox[r] + ((size_t)par * kArMaxW + rank) * p.max_tensors + t), "f"(me) : "memory");
+      }
+      for (int t = threadIdx.x; t < p.max_tensors; t += kArThreads) amax_next[t] = 0u;
+      __syncthreads();
+    }
+    signal_peers(p, 1, epoch);
+    wait_peers(p, 1, epoch);
+    stamp(p, 4);
+    for (int t = threadIdx.x; t < p.T; t += kArThreads) {
+      float me = -INFINITY;
+      for (int r = 0; r < W; ++r) {
+        const float v = ld_sys_f32(p.mailbox[rank] + ((size_t)par * kArMaxW + r) * p.max_tensors + t);
+        me = (v != v || me != me) ? NAN : fmaxf(me, v);
+      }
+      const int sh = aps_shift_from_exponent(me, fmt.exp_bits());
+      s_shift[t] = sh;
+      if (p.shifts_out && blockIdx.x == 0) p.shifts_out[t] = sh;
+    }
+    __syncthreads();
+    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
+      const Chunk ck = p.chunks[c];
+      const int sh = s_shift[ck.tensor];
+      const float sc = pow2i(sh), inv = pow2i(-sh);
+      // 4 elements per thread per step, all W peers' vectors requested before the first use
+      for (int v4 = threadIdx.x; v4 < (ck.len >> 2); v4 += kArThreads) {
+        const long long e0 = ck.start + 4 * v4;
+        uint4 in[kArMaxW];
+#pragma unroll
+        for (int r = 0; r < kArMaxW; ++r)
+          if (r < W) in[r] = ld_sys_u4(p.data[r] + par * p.cap_bytes + e0 * 4);
+        float s4[4] = {0.f, 0.f, 0.f, 0.f}, c4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < kArMaxW; ++r) {
+          if (r < W) {
+            const float x[4] = {__uint_as_float(in[r].x), __uint_as_float(in[r].y), __uint_as_float(in[r].z), __uint_as_float(in[r].w)};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float v = fmt.q(x[i] * sc);
+              if (KAHAN) fold_kahan_members(fmt, s4[i], c4[i], v);
+              else fold_plain_members(fmt, s4[i], v);
+            }
+          }
+        }
+        *reinterpret_cast<float4*>(p.grad + e0) = make_float4(s4[0] * inv, s4[1] * inv, s4[2] * inv, s4[3] * inv);
+      }
+    }
+    stamp(p, 7);
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.ws[2] = epoch;
+    return;
+  }
+
   // ---------------- phase A: per-tensor amax, exponent exchange ---------------------
   if (p.use_aps) {
     // contiguous chunk range per CTA: consecutive chunks mostly belong to the same tensor, so the
@@ -278,6 +360,9 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
       const int sh = aps_shift_from_exponent(me, fmt.exp_bits());
       s_shift[t] = sh;
       if (p.shifts_out && blockIdx.x == 0) p.shifts_out[t] = sh;
+      // guard counters: tensors whose global max is Inf/NaN, and all-zero tensors, since the first launch
+      if (blockIdx.x == 0 && (me != me || me == INFINITY)) atomicAdd(p.ws + 4 + 2 * p.max_tensors + 16, 1u);
+      if (blockIdx.x == 0 && me == -INFINITY) atomicAdd(p.ws + 4 + 2 * p.max_tensors + 17, 1u);
     }
     __syncthreads();
   }
@@ -447,6 +532,7 @@ void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunk
   p.ident = (e == 8 && m == 23 && !kahan) ? 1 : 0;
   p.ws = local_ws; p.shifts_out = shifts_out; p.timeout = timeout_cycles;
   if (p.algo == ALGO_NVLS && !cb.mc_gather) p.algo = ALGO_TWOSHOT;
+  if (p.algo == ALGO_ONESHOT_RAW && !use_aps) p.algo = ALGO_ONESHOT;     // without APS the fp32-wire one-shot already needs one round
   // two co-resident CTAs per SM (<= 128 registers by launch bounds): 16 warps / SM keep enough 128-bit
   // loads in flight to cover HBM / NVLink latency; the grid barrier needs all CTAs resident
   int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1) * 2;

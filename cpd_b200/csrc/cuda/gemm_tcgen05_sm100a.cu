@@ -254,7 +254,8 @@ int gemm_tc_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, i
                  int operand_mode, const float* bias, int variant, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   // CTA-pair kernel when it covers the format and its 256x256 tiles still fill the machine
-  if (variant == 2 || (variant == 0 && 2 * ((M + 255) / 256) * ((N + 255) / 256) >= device_sm_count(-1))) {
+  // (Kahan's four casts per element make the kernel requant-bound either way; measured slightly faster on 128x128 tiles)
+  if (variant == 2 || (variant == 0 && !kahan && 2 * ((M + 255) / 256) * ((N + 255) / 256) >= device_sm_count(-1))) {
     const int rc = gemm_tc2_cuda(A, Bt, C, M, N, K, e, m, kahan, k_slice, operand_mode, bias, st);
     if (rc == 0 || variant == 2) return rc;
   }

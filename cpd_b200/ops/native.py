@@ -24,7 +24,7 @@ ALIGN_ELEMS = 16            # tensors start on 64-byte boundaries inside an aren
 CHUNK_DTYPE = np.dtype([("start", "<i8"), ("len", "<i4"), ("tensor", "<i4")])
 assert CHUNK_DTYPE.itemsize == _C.chunk_struct_size()
 
-ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS = 0, 1, 2, 3
+ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_ONESHOT_RAW = 0, 1, 2, 3, 4
 
 
 def rounding_code(rounding) -> int:

@@ -29,7 +29,7 @@ from ..ops import native
 from .arena import ChunkTable, ModelArena
 
 _ALGO = {"auto": native.ALGO_AUTO, "oneshot": native.ALGO_ONESHOT, "twoshot": native.ALGO_TWOSHOT,
-         "nvls": native.ALGO_NVLS}
+         "nvls": native.ALGO_NVLS, "raw": native.ALGO_ONESHOT_RAW}
 
 # packed bytes per bucket below which the one-shot variant (1 exchange fewer, W x the
 # fold work and (W-1)/1 x the NVLink reads) beats two-shot; tuned on 8xB200
@@ -37,6 +37,7 @@ _FAULT_DELAY_RANK = int(os.environ.get("CPD_B200_FAULT_DELAY_RANK", "-1"))
 _FAULT_DELAY_CYCLES = float(os.environ.get("CPD_B200_FAULT_DELAY_CYCLES", "2e8"))
 ONESHOT_MAX_BYTES = 1024 * 1024     # measured on 8xB200: one-shot 58 us vs two-shot 72 us at 1 MB packed, 126 vs 99 us at 4 MB
 MAX_TENSORS_PER_BUCKET = 1024
+RAW_MAX_ELEMS = 64 * 1024            # single-round raw-fp32 variant below 256 KB of gradients
 
 
 class GradReducer:
@@ -91,7 +92,10 @@ class GradReducer:
             self.local_ws = torch.zeros(4 + 2 * MAX_TENSORS_PER_BUCKET + 32, dtype=torch.int32, device=self.device)
         if self.mode == "fused":
             from .symm import SymmetricWorkspace
-            self.symm = SymmetricWorkspace(self.max_numel * (self.wire // 8), MAX_TENSORS_PER_BUCKET, group=group)
+            cap = max(self.max_numel * (self.wire // 8), min(self.max_numel, RAW_MAX_ELEMS) * 4)
+            if cfg.algo == "raw":
+                cap = self.max_numel * 4
+            self.symm = SymmetricWorkspace(cap, MAX_TENSORS_PER_BUCKET, group=group)
         elif self.mode == "gather" and self.world > 1:
             self._gather_buf = torch.empty(self.world, self.max_numel, dtype=torch.float32, device=self.device)
 
@@ -112,6 +116,8 @@ class GradReducer:
         if a != native.ALGO_AUTO:
             return a
         nbytes = b.numel * (self.wire // 8)
+        if self.cfg.use_aps and b.numel <= RAW_MAX_ELEMS:
+            return native.ALGO_ONESHOT_RAW              # latency-bound: one flag round, raw fp32 on the wire
         if self.world <= 2 or nbytes <= ONESHOT_MAX_BYTES:
             return native.ALGO_ONESHOT
         return native.ALGO_NVLS if (self.symm is not None and self.symm.has_multicast) else native.ALGO_TWOSHOT
@@ -227,6 +233,15 @@ class GradReducer:
         d = lambda a, b: round((t[b] - t[a]) / 1e3, 2) if t[a] and t[b] and t[b] >= t[a] else None  # noqa: E731
         return {"A_amax+gridbar": d(0, 1), "exp_exchange": d(1, 2), "B_pack+gridbar": d(2, 3), "data_flags": d(3, 4), "C_fold": d(4, 5),
                 "gather_gridbar+flags": d(5, 6), "D_unpack": d(6, 7) if t[6] else None, "total": d(0, 7)}
+
+    def guard_counters(self) -> dict:
+        """Cumulative counters kept by the fused kernel: tensors whose cross-rank max |g| was Inf/NaN (their shift is
+        forced to 0 and the non-finite values propagate) and all-zero tensors (shift 0 instead of the reference's NaN)."""
+        if self.local_ws is None or self.mode != "fused":
+            return {}
+        base = 4 + 2 * MAX_TENSORS_PER_BUCKET + 16
+        c = self.local_ws[base:base + 2].cpu().tolist()
+        return {"nonfinite_tensor_events": int(c[0]), "all_zero_tensor_events": int(c[1])}
 
     def remove_hooks(self) -> None:
         for h in self._hooks:

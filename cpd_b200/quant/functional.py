@@ -107,7 +107,7 @@ def quant_gemm(a: torch.Tensor, b: torch.Tensor, man: int = 23, exp: int = 8, mo
     M, K = a.shape
     N = b.shape[1]
     if mode == "auto":
-        mode = "tile" if (a.is_cuda and M * N * K >= _TILE_MIN_WORK and K % 16 == 0) else "exact"
+        mode = "tile" if (a.is_cuda and M * N * K >= _TILE_MIN_WORK) else "exact"
     if mode == "exact":
         out = native.gemm_exact(a, b, exp, man, rounding, True if kahan is None else kahan)
         if bias is not None:
@@ -117,6 +117,10 @@ def quant_gemm(a: torch.Tensor, b: torch.Tensor, man: int = 23, exp: int = 8, mo
         raise ValueError(f"unknown gemm mode {mode!r}")
     if not a.is_cuda:
         raise NotImplementedError("mode='tile' needs a CUDA device (use ops.native.gemm_tile_cpu for the CPU model)")
+    if K % 16:      # TMA needs 16-byte aligned rows: zero-pad K (e.g. the 3x3x3 = 27 wide im2col of a first conv layer)
+        padk = 16 - K % 16
+        a = torch.nn.functional.pad(a, (0, padk))
+        b = torch.nn.functional.pad(b, (0, 0, 0, padk))
     if operands in ("mxe4m3", "mxe5m2"):       # block-scaled fp8 operands (one power-of-two scale per 32 K-elements)
         e5 = operands == "mxe5m2"
         ac, asf = native.mx_quantize(a.contiguous(), e5)

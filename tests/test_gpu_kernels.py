@@ -284,3 +284,16 @@ def test_quant_gemm_mx_operands():
     c = quant_gemm(a, b, man=10, exp=5, mode="tile", operands="mxe4m3", k_slice=256)
     ref = a @ b
     assert (c - ref).abs().max() / ref.abs().max() < 0.06
+
+
+def test_quant_conv_tile_mode_first_layer_k27():
+    """K = 27 (3x3x3 im2col) is zero-padded for the TMA path; result close to fp32 conv."""
+    from cpd_b200 import Quant_Conv
+    torch.manual_seed(0)
+    qc = Quant_Conv(3, 64, 3, padding=1, bias=True, exp=5, man=10, mode="tile").cuda()
+    x = torch.randn(64, 3, 32, 32, device="cuda", requires_grad=True)
+    y = qc(x)
+    ref = torch.nn.functional.conv2d(x, qc.weight, qc.bias, padding=1)
+    assert (y - ref).abs().max() / ref.abs().max() < 3e-2
+    y.sum().backward()
+    assert torch.isfinite(qc.weight.grad).all() and torch.isfinite(x.grad).all()

@@ -121,7 +121,9 @@ def section_correct(rank, world, res):
             else:
                 oracle.reduce()
                 want = arena.grad_flat.clone()
-            for algo in ("oneshot", "twoshot", "nvls"):
+            for algo in ("oneshot", "twoshot", "nvls", "raw"):
+                if algo == "raw" and (not kw.get("use_aps") or arena.layout.total > (1 << 22)):
+                    continue
                 fused = GradReducer(arena, PrecisionConfig(algo=algo, **kw), mode="fused")
                 if algo == "nvls" and not fused.symm.has_multicast:
                     continue
@@ -194,8 +196,10 @@ def section_sweep(rank, world, res, max_bytes):
         fill(arena, rank, seed=3, scale_lo=-8, scale_hi=-2)
         iters = 200 if nbytes <= (1 << 20) else (40 if nbytes <= (1 << 26) else 8)
         row = dict(fp32_bytes=nbytes, elems=n)
-        for algo in ("oneshot", "twoshot", "nvls"):
+        for algo in ("raw", "oneshot", "twoshot", "nvls"):
             if algo == "oneshot" and nbytes > (1 << 26):
+                continue
+            if algo == "raw" and nbytes > (1 << 22):
                 continue
             red = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, algo=algo), mode="fused")
             if algo == "nvls" and not red.symm.has_multicast:
