@@ -198,12 +198,6 @@ struct FormatT {
   }
 };
 
-// Runtime-format functor with the same interface as FormatT.
-struct FormatR {
-  Format f;
-  CPD_HD float q(float x) const { return quantize(x, f); }
-};
-
 // ---- accumulation steps ----------------------------------------------------
 // Plain:  s = Q(s + v)
 // Kahan:  y = Q(v - c); t = Q(s + y); c = Q(Q(t - s) - y); s = t

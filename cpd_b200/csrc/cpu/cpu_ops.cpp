@@ -55,7 +55,7 @@ void quantize_scaled_cpu(const float* in, float* out, int64_t n, int e, int m, i
 void gemm_exact_cpu(const float* A, int64_t sa0, int64_t sa1, const float* B, int64_t sb0, int64_t sb1,
                     float* C, int64_t ldc, int M, int N, int K, int e, int m, int rounding, bool kahan) {
   const Format f = make_format(e, m, rounding);
-  FormatR q{f};
+  FmtR q{f};
   const int64_t grain = std::max<int64_t>(1, (1 << 14) / std::max<int64_t>(1, (int64_t)N * K));
   parallel_for(M, grain, [=](int64_t r0, int64_t r1) {
   for (int64_t i = r0; i < r1; ++i) {
@@ -81,7 +81,7 @@ void gemm_tile_cpu(const float* A, int64_t sa0, int64_t sa1, const float* B, int
   const Format f = make_format(e, m, rounding);
   const Format fo = make_format(op_e, op_m, ROUND_IEEE);
   const bool round_ops = !(op_e == 8 && op_m == 23);
-  FormatR q{f};
+  FmtR q{f};
   if (k_slice <= 0) k_slice = K;
   const int64_t grain = std::max<int64_t>(1, (1 << 14) / std::max<int64_t>(1, (int64_t)N * K));
   parallel_for(M, grain, [=](int64_t r0, int64_t r1) {
@@ -116,7 +116,7 @@ void gemm_tile_cpu(const float* A, int64_t sa0, int64_t sa1, const float* B, int
 void aps_fold_cpu(const float* const* srcs, int W, float* out, const int64_t* seg_off, int T, int e,
                   int m, int rounding, bool use_aps, bool kahan, float world_mult, int* shifts_out) {
   const Format f = make_format(e, m, rounding);
-  FormatR q{f};
+  FmtR q{f};
   const bool ident = is_identity(e, m) && !kahan;
   for (int t = 0; t < T; ++t) {
     const int64_t b = seg_off[t], en = seg_off[t + 1];

@@ -22,6 +22,21 @@ if which in ("all", "gemm_tc"):
     a8, b8 = a.to(torch.float8_e4m3fn), bt.to(torch.float8_e4m3fn)
     for _ in range(3):
         native.gemm_tc(a8, b8, 4, 3, kahan=False, k_slice=512, operand_mode=native.OPERAND_E4M3)
+if which in ("gemm_exact",):
+    a, b = torch.randn(1024, 1024, device="cuda"), torch.randn(1024, 1024, device="cuda")
+    for _ in range(2):
+        native.gemm_exact(a, b, 4, 3)
+if which in ("mx",):
+    a, bt = torch.randn(4096, 4096, device="cuda"), torch.randn(4096, 4096, device="cuda")
+    for _ in range(2):
+        ac, asf = native.mx_quantize(a)
+        bc, bsf = native.mx_quantize(bt)
+        native.gemm_tc_mx(ac, asf, bc, bsf, 5, 10, k_slice=512)
+if which in ("quantize",):
+    x = torch.randn(1 << 26, device="cuda")
+    o = torch.empty_like(x)
+    for _ in range(3):
+        native.quantize_(x, o, 4, 3)
 if which in ("gemm_tc2",):
     M = N = K = 8192
     a = torch.randn(M, K, device="cuda").bfloat16()

@@ -42,26 +42,31 @@ def ncu_summary(rep, out_md):
         lines.append("")
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     srows = list(csv.reader(src.splitlines()))
-    if len(srows) > 2:
-        SH = srows[0]
-        def col(*names):
-            for n in names:
-                if n in SH:
-                    return SH.index(n)
-            return None
-        ci, cs, cw = col("Source"), col("Warp Stall Sampling (All Samples)", "Warp Stall Sampling (All Cycles)"), col("# Instructions Executed", "Instructions Executed")
-        if ci is not None and cs is not None:
-            top = []
-            for r in srows[1:]:
-                try:
-                    top.append((float(r[cs].replace(",", "") or 0), r[ci][:110], r[cw] if cw is not None else ""))
-                except (ValueError, IndexError):
-                    pass
-            top.sort(reverse=True)
-            tot = sum(t[0] for t in top) or 1
-            lines += ["## hottest source lines (warp-stall samples, first captured launch)", "", "| % of samples | instructions | source |", "|---|---|---|"]
-            for s, t, w in top[:14]:
-                lines.append(f"| {100 * s / tot:.1f} | {w} | `{t.strip()}` |")
+    hdrs = [i for i, r in enumerate(srows) if len(r) > 3 and r[0] == "Address"]
+    if hdrs:
+        hi = hdrs[0]
+        SH = srows[hi]
+        end = hdrs[1] - 1 if len(hdrs) > 1 else len(srows)
+        try:
+            cs, ci, cn = SH.index("Warp Stall Sampling (All Samples)"), SH.index("Source"), SH.index("Instructions Executed")
+        except ValueError:
+            cs = None
+        if cs is not None:
+            data = [r for r in srows[hi + 1:end] if len(r) == len(SH)]
+            tot = sum(float(r[cs] or 0) for r in data) or 1.0
+            top = sorted(((float(r[cs] or 0), r[ci].strip()[:90], r[cn]) for r in data), reverse=True)[:16]
+            byop = {}
+            for r in data:
+                t = r[ci].strip().split()
+                if not t:
+                    continue
+                op = (t[1] if t[0].startswith("@") and len(t) > 1 else t[0]).split(".")[0]
+                byop[op] = byop.get(op, 0.0) + float(r[cs] or 0)
+            lines += [f"## warp-stall samples by SASS instruction (first captured launch, {len(data)} instructions)", "",
+                      "by opcode: " + ", ".join(f"{k} {100 * v / tot:.1f}%" for k, v in sorted(byop.items(), key=lambda kv: -kv[1])[:12]), "",
+                      "| % of samples | executed | instruction |", "|---|---|---|"]
+            for sv, t, n in top:
+                lines.append(f"| {100 * sv / tot:.1f} | {n} | `{t}` |")
             lines.append("")
     open(out_md, "w").write("\n".join(lines) + "\n")
     return True
@@ -100,7 +105,7 @@ def sweep_md(js, out_md):
     lines = [f"# low-bit all-reduce sweep, {W} x B200 ((4,3) + APS, 8-bit wire)", "",
              "Device-timed (CUDA events, max over ranks).  busbw = fp32 payload / t * 2(W-1)/W (nccl-tests convention).  Roofline for the fused kernel = slower of",
              "(wire bytes that must cross NVLink per GPU / 770 GB/s measured) and (local HBM traffic ~ 13 B/element / measured copy bandwidth).", "",
-             "| fp32 bytes | fused one-shot us | fused two-shot us | fused NVLS us | fused Kahan us | NCCL fp32 all_reduce us | reference algorithm us | best fused busbw GB/s | NCCL busbw GB/s | reference busbw GB/s | fused roofline us | fused / roofline |",
+             "| fp32 bytes | fused one-shot (best of packed / raw) us | fused two-shot us | fused NVLS us | fused Kahan us | NCCL fp32 all_reduce us | reference algorithm us | best fused busbw GB/s | NCCL busbw GB/s | reference busbw GB/s | fused roofline us | fused / roofline |",
              "|---|---|---|---|---|---|---|---|---|---|---|---|"]
     try:
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -108,12 +113,12 @@ def sweep_md(js, out_md):
         hbm = 6650.0
     for r in rows:
         n = r["elems"]
-        best = min(v for k, v in r.items() if k.startswith("fused_") and k.endswith("_us") and "kahan" not in k)
+        best = min(v for k, v in r.items() if k.startswith("fused_") and k.endswith("_us") and "kahan" not in k and "phases" not in k)
         link_us = (2 * (W - 1) / W * n * 1) / (NVLINK_MEASURED_GBS * 1e3)          # two-shot wire bytes per GPU per direction
         hbm_us = (13.0 * n) / (hbm * 1e3)
         roof = max(link_us, hbm_us)
         bw = max(v for k, v in r.items() if k.startswith("fused_") and k.endswith("busbw_fp32_GBps"))
-        lines.append(f"| {r['fp32_bytes']} | {r.get('fused_oneshot_us', '-')} | {r.get('fused_twoshot_us', '-')} | {r.get('fused_nvls_us', '-')} | {r.get('fused_auto_kahan_us', '-')} | "
+        lines.append(f"| {r['fp32_bytes']} | {min(r.get('fused_oneshot_us', 1e9), r.get('fused_raw_us', 1e9)) if ('fused_oneshot_us' in r or 'fused_raw_us' in r) else '-'} | {r.get('fused_twoshot_us', '-')} | {r.get('fused_nvls_us', '-')} | {r.get('fused_auto_kahan_us', '-')} | "
                      f"{r.get('nccl_fp32_allreduce_us', '-')} | {r.get('reference_algo_us', '-')} | {bw} | {r.get('nccl_fp32_busbw_GBps', '-')} | {r.get('reference_algo_busbw_fp32_GBps', '-')} | "
                      f"{roof:.2f} | {roof / best:.3f} |")
     open(out_md, "w").write("\n".join(lines) + "\n")
