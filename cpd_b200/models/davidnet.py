@@ -92,3 +92,75 @@ def davidnet(channels=(64, 128, 256, 512), num_classes: int = 10, logit_scale: f
     nodes.append(("linear", nn.Linear(channels[3], num_classes, bias=False), ["flatten"]))
     nodes.append(("logits", Scale(logit_scale), ["linear"]))
     return GraphNet(nodes, ["logits"])
+
+
+# ---- dict-described networks (the reference's DavidNet is written this way) ------------------------------
+class Identity(nn.Module):
+    def forward(self, x):
+        return x
+
+
+class Concat(nn.Module):
+    def forward(self, *xs):
+        return torch.cat(xs, 1)
+
+
+class Correct(nn.Module):
+    def forward(self, logits, target):
+        return logits.max(dim=1)[1] == target
+
+
+class RelPath(tuple):
+    """Input reference relative to the enclosing dict, e.g. ``rel('in')`` or ``rel('res2', 'relu')``."""
+
+
+def rel(*parts) -> RelPath:
+    return RelPath(parts)
+
+
+def graph_from_nested(spec: dict, outputs: Sequence[str], sep: str = "_") -> GraphNet:
+    """Build a :class:`GraphNet` from a nested-dict description (reference: example/DavidNet/davidnet.py:19-69 with
+    the interpreter of utils.py:233-292).  Leaves are ``module`` or ``(module, [inputs])``; a leaf without explicit
+    inputs consumes the previous leaf (the first one consumes ``"input"``); inputs are absolute names, tuples of path
+    parts, or ``rel(...)`` paths resolved against the leaf's enclosing dict."""
+    leaves: List[Tuple[Tuple[str, ...], object]] = []
+
+    def walk(d, pfx):
+        for k, v in d.items():
+            if isinstance(v, dict):
+                walk(v, pfx + (k,))
+            else:
+                leaves.append((pfx + (k,), v))
+
+    walk(spec, ())
+    nodes, prev = [], "input"
+    for path, val in leaves:
+        name = sep.join(path)
+        if isinstance(val, tuple):
+            mod, ins = val
+            resolved = []
+            for i in ins:
+                if isinstance(i, RelPath):
+                    resolved.append(sep.join(path[:-1] + tuple(i)))
+                elif isinstance(i, tuple):
+                    resolved.append(sep.join(i))
+                else:
+                    resolved.append(i)
+        else:
+            mod, resolved = val, [prev]
+        nodes.append((name, mod, resolved))
+        prev = name
+    return GraphNet(nodes, outputs)
+
+
+def batch_norm(num_channels, bn_bias_init=None, bn_bias_freeze=False, bn_weight_init=None, bn_weight_freeze=False):
+    m = nn.BatchNorm2d(num_channels)
+    if bn_bias_init is not None:
+        m.bias.data.fill_(bn_bias_init)
+    if bn_bias_freeze:
+        m.bias.requires_grad = False
+    if bn_weight_init is not None:
+        m.weight.data.fill_(bn_weight_init)
+    if bn_weight_freeze:
+        m.weight.requires_grad = False
+    return m

@@ -167,3 +167,29 @@ def test_aps_optimizer_hook_runner_interface():
     from cpd_b200 import float_quantize
     g = model.weight.grad
     assert torch.isfinite(g).all()
+
+
+def test_graphnet_from_nested_dict_matches_builtin_davidnet():
+    import torch.nn as nn
+    from cpd_b200.models import davidnet, graph_from_nested, rel, Add, Scale, Identity, Correct
+
+    def conv_bn(cin, cout):
+        return {"conv": nn.Conv2d(cin, cout, 3, padding=1, bias=False), "bn": nn.BatchNorm2d(cout), "relu": nn.ReLU(True)}
+
+    def residual(c):
+        return {"in": Identity(), "res1": conv_bn(c, c), "res2": conv_bn(c, c), "add": (Add(), [rel("in"), rel("res2", "relu")])}
+
+    spec = {"prep": conv_bn(3, 64),
+            "layer1": dict(conv_bn(64, 128), pool=nn.MaxPool2d(2), residual=residual(128)),
+            "layer2": dict(conv_bn(128, 256), pool=nn.MaxPool2d(2)),
+            "layer3": dict(conv_bn(256, 512), pool=nn.MaxPool2d(2), residual=residual(512)),
+            "classifier": {"pool": nn.MaxPool2d(4), "flatten": nn.Flatten(1), "linear": nn.Linear(512, 10, bias=False), "logits": Scale(0.125)},
+            "correct": (Correct(), [("classifier", "logits"), "target"])}
+    g = graph_from_nested({k: v for k, v in spec.items() if k != "correct"}, ["classifier_logits"])
+    ref = davidnet()
+    assert sum(p.numel() for p in g.parameters()) == sum(p.numel() for p in ref.parameters()) == 6573120
+    assert len(list(g.parameters())) == 25
+    g.load_state_dict({k2: v for (k2, _), v in zip(g.state_dict().items(), ref.state_dict().values())})
+    x = torch.randn(2, 3, 32, 32)
+    g.eval(); ref.eval()
+    assert torch.allclose(g(x), ref(x), atol=1e-5)
