@@ -260,9 +260,11 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
         for (int r = 0; r < kArMaxW; ++r)
           if (r < W) in[r] = ld_sys_u4(p.data[r] + par * p.cap_bytes + e0 * 4);
         float s4[4] = {0.f, 0.f, 0.f, 0.f}, c4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int r = 0; r < kArMaxW; ++r) {
-          if (r < W) {
+        // rolled on purpose (the peers' vectors sit in a small local array): unrolling the casts over 8 ranks
+        // multiplies the code size and the cold instruction-cache misses dominate a latency-bound launch
+#pragma unroll 1
+        for (int r = 0; r < W; ++r) {
+          {
             const float x[4] = {__uint_as_float(in[r].x), __uint_as_float(in[r].y), __uint_as_float(in[r].z), __uint_as_float(in[r].w)};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -384,23 +386,17 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
     if (a1) load16(p.grad + e1, x1);
     if (a0) {
       const float sc = p.use_aps ? pow2i(s_shift[ck0.tensor]) : 1.f;
-      if (p.use_aps) {
+      if (p.use_aps || p.prequant) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) x0[i] = fmt.q(x0[i] * sc);
-      } else if (p.prequant) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x0[i] = fmt.q(x0[i]);
       }
       granule_store<WIRE>(my_data, e0, granule_encode<WIRE>(fmt, x0), false);
     }
     if (a1) {
       const float sc = p.use_aps ? pow2i(s_shift[ck1.tensor]) : 1.f;
-      if (p.use_aps) {
+      if (p.use_aps || p.prequant) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) x1[i] = fmt.q(x1[i] * sc);
-      } else if (p.prequant) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x1[i] = fmt.q(x1[i]);
       }
       granule_store<WIRE>(my_data, e1, granule_encode<WIRE>(fmt, x1), false);
     }
@@ -432,9 +428,12 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
       float s[16], cc[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) { s[i] = 0.f; cc[i] = 0.f; }
-#pragma unroll
-      for (int r = 0; r < kArMaxW; ++r) {
-        if (r < W) {
+      // the rank loop is deliberately NOT unrolled: the loads above are all in flight already, and 8 unrolled copies
+      // of decode + 16 casts (with their cold paths) made this kernel ~180 KB of SASS — at W = 8 the cold
+      // instruction-cache misses cost ~20 us per launch (measured: phase C of a 1 KB message 26 us -> see profiles/)
+#pragma unroll 1
+      for (int r = 0; r < W; ++r) {
+        {
           float v[16];
           if (WIRE <= 16) granule_decode<WIRE>(fmt, in[r % kPre], v);
           else granule_decode<WIRE>(fmt, granule_load_sys<WIRE>(p.data[r] + par * p.cap_bytes, e0), v);
