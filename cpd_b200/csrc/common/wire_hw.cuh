@@ -23,11 +23,24 @@ template <class F>
 struct FoldOps {
   static constexpr bool kHw = false;
   static __device__ __forceinline__ float qsum(const F& f, float x) { return f.q(x); }
+  template <int N>
+  static __device__ __forceinline__ void qsum_n(const F& f, float (&x)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = f.q(x[i]);
+  }
   static __device__ __forceinline__ void decode4(const F& f, uint32_t w, float (&o)[4]) {
     o[0] = f.unpack(w & 0xFFu); o[1] = f.unpack((w >> 8) & 0xFFu); o[2] = f.unpack((w >> 16) & 0xFFu); o[3] = f.unpack(w >> 24);
   }
   static __device__ __forceinline__ uint32_t encode4(const F& f, const float (&x)[4]) {
     return f.pack(x[0]) | (f.pack(x[1]) << 8) | (f.pack(x[2]) << 16) | (f.pack(x[3]) << 24);
+  }
+  static __device__ __forceinline__ void decode16(const F& f, const uint32_t (&w)[4], float (&x)[16]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float o[4];
+      decode4(f, w[k], o);
+      x[4 * k] = o[0]; x[4 * k + 1] = o[1]; x[4 * k + 2] = o[2]; x[4 * k + 3] = o[3];
+    }
   }
 };
 
@@ -50,6 +63,30 @@ struct FoldOpsFp8 {
     }
     return f.q(x);                                    // NaN / Inf / quirk band: exact software cast
   }
+  // out-of-line exact cast for the rare lanes of the wide version below (keeps its cold block to one CALL per element)
+  static __device__ __noinline__ float qsum_cold(float x) { return FormatT<E_BITS, M_BITS>::q(x); }
+  // N casts behind ONE guard: the NaN-propagating maximum of the magnitudes is below the limit iff every element is a
+  // finite value below the quirk band, and then all N go through paired converts with no per-element control flow
+  // (per element: 1 FMNMX + 1/2 F2FP pack + 1/2 F2FP unpack + 1 HADD2.F32, against ~11 instructions and one
+  // data-dependent branch for the scalar form — the branch latency, not the ALU work, bounded a lone warp).
+  template <int N>
+  static __device__ __forceinline__ void qsum_n(const F& f, float (&x)[N]) {
+    static_assert(N % 2 == 0, "pairs");
+    float g = fabsf(x[0]);
+#pragma unroll
+    for (int i = 1; i < N; ++i) asm("max.NaN.f32 %0, %0, %1;" : "+f"(g) : "f"(fabsf(x[i])));
+    if (g < kLimit) {                                 // false when any element is NaN
+#pragma unroll
+      for (int i = 0; i < N; i += 2) {
+        const __nv_fp8x2_storage_t c = __nv_cvt_float2_to_fp8x2(make_float2(x[i], x[i + 1]), __NV_SATFINITE, INTERP);
+        const float2 r = __half22float2(__half2(__nv_cvt_fp8x2_to_halfraw2(c, INTERP)));
+        x[i] = r.x; x[i + 1] = r.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] = qsum_cold(x[i]);
+    }
+  }
   static __device__ __forceinline__ void decode4(const F& f, uint32_t w, float (&o)[4]) {
     if ((((w & kExpMask32) + kCarry32) & 0x80808080u) == 0u) {          // no reserved (all-ones exponent) code among the 4
       const __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w & 0xFFFFu), INTERP);
@@ -60,6 +97,26 @@ struct FoldOpsFp8 {
       o[0] = f.unpack(w & 0xFFu); o[1] = f.unpack((w >> 8) & 0xFFu); o[2] = f.unpack((w >> 16) & 0xFFu); o[3] = f.unpack(w >> 24);
     }
   }
+  // one granule (16 codes) behind one reserved-code test
+  static __device__ __forceinline__ void decode16(const F& f, const uint32_t (&w)[4], float (&x)[16]) {
+    const uint32_t any = (((w[0] & kExpMask32) + kCarry32) | ((w[1] & kExpMask32) + kCarry32) |
+                          ((w[2] & kExpMask32) + kCarry32) | ((w[3] & kExpMask32) + kCarry32)) & 0x80808080u;
+    if (any == 0u) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = __half22float2(__half2(__nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w[k] & 0xFFFFu), INTERP)));
+        const float2 b = __half22float2(__half2(__nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w[k] >> 16), INTERP)));
+        x[4 * k] = a.x; x[4 * k + 1] = a.y; x[4 * k + 2] = b.x; x[4 * k + 3] = b.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[4 * k + j] = unpack_cold((w[k] >> (8 * j)) & 0xFFu);
+      }
+    }
+  }
+  static __device__ __noinline__ float unpack_cold(uint32_t c) { return wire_unpack(c, E_BITS, wire_man(M_BITS)); }
   static __device__ __forceinline__ uint32_t encode4(const F& f, const float (&x)[4]) {
     const float m = fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3])));
     const bool nan = (x[0] != x[0]) | (x[1] != x[1]) | (x[2] != x[2]) | (x[3] != x[3]);
@@ -84,6 +141,32 @@ __device__ __forceinline__ void fold_kahan_members(const F& f, float& s, float& 
   const float t = FoldOps<F>::qsum(f, s + y);
   c = FoldOps<F>::qsum(f, FoldOps<F>::qsum(f, t - s) - y);
   s = t;
+}
+
+// the same two steps over N accumulators at once (one guard per cast stage instead of one per element)
+template <class F, int N>
+__device__ __forceinline__ void fold_plain_members_n(const F& f, float (&s)[N], const float (&v)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] += v[i];
+  FoldOps<F>::template qsum_n<N>(f, s);
+}
+template <class F, int N>
+__device__ __forceinline__ void fold_kahan_members_n(const F& f, float (&s)[N], float (&c)[N], const float (&v)[N]) {
+  float y[N], t[N], d[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = v[i] - c[i];
+  FoldOps<F>::template qsum_n<N>(f, y);
+#pragma unroll
+  for (int i = 0; i < N; ++i) t[i] = s[i] + y[i];
+  FoldOps<F>::template qsum_n<N>(f, t);
+#pragma unroll
+  for (int i = 0; i < N; ++i) d[i] = t[i] - s[i];
+  FoldOps<F>::template qsum_n<N>(f, d);
+#pragma unroll
+  for (int i = 0; i < N; ++i) d[i] -= y[i];
+  FoldOps<F>::template qsum_n<N>(f, d);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { c[i] = d[i]; s[i] = t[i]; }
 }
 
 }  // namespace cpd

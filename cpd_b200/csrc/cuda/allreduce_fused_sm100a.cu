@@ -105,12 +105,7 @@ __device__ __forceinline__ void granule_decode(const F& fmt, const Granule<WIRE>
     }
   } else {
     const unsigned w[4] = {g.v[0].x, g.v[0].y, g.v[0].z, g.v[0].w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float o[4];
-      FoldOps<F>::decode4(fmt, w[k], o);          // hardware E4M3/E5M2 unpack where the codes allow it
-      x[4 * k + 0] = o[0]; x[4 * k + 1] = o[1]; x[4 * k + 2] = o[2]; x[4 * k + 3] = o[3];
-    }
+    FoldOps<F>::decode16(fmt, w, x);              // hardware E4M3/E5M2 unpack where the codes allow it
   }
 }
 template <int WIRE, class F>
@@ -260,18 +255,16 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
         for (int r = 0; r < kArMaxW; ++r)
           if (r < W) in[r] = ld_sys_u4(p.data[r] + par * p.cap_bytes + e0 * 4);
         float s4[4] = {0.f, 0.f, 0.f, 0.f}, c4[4] = {0.f, 0.f, 0.f, 0.f};
-        // rolled on purpose (the peers' vectors sit in a small local array): unrolling the casts over 8 ranks
-        // multiplies the code size and the cold instruction-cache misses dominate a latency-bound launch
+        // rolled on purpose (the peers' vectors sit in a small local array): unrolling over 8 ranks only multiplies the code
 #pragma unroll 1
         for (int r = 0; r < W; ++r) {
           {
-            const float x[4] = {__uint_as_float(in[r].x), __uint_as_float(in[r].y), __uint_as_float(in[r].z), __uint_as_float(in[r].w)};
+            float v[4] = {__uint_as_float(in[r].x) * sc, __uint_as_float(in[r].y) * sc, __uint_as_float(in[r].z) * sc,
+                          __uint_as_float(in[r].w) * sc};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float v = fmt.q(x[i] * sc);
-              if (KAHAN) fold_kahan_members(fmt, s4[i], c4[i], v);
-              else fold_plain_members(fmt, s4[i], v);
-            }
+            for (int i = 0; i < 4; ++i) v[i] = fmt.q(v[i]);
+            if (KAHAN) fold_kahan_members_n(fmt, s4, c4, v);
+            else fold_plain_members_n(fmt, s4, v);
           }
         }
         *reinterpret_cast<float4*>(p.grad + e0) = make_float4(s4[0] * inv, s4[1] * inv, s4[2] * inv, s4[3] * inv);
@@ -416,6 +409,8 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
     const float inv = p.use_aps ? pow2i(-s_shift[ck.tensor]) : 1.f;
     for (int g = threadIdx.x; g < (ck.len >> 4); g += kArThreads) {
       const long long e0 = ck.start + 16 * g;
+      const bool first = c == c_begin && g == (int)threadIdx.x;      // finer stamps of CTA 0's first granule (slots 9..12)
+      if (first) stamp(p, 9);
       // narrow wires: issue all W peer loads before the first use (W x 16..32 B in flight
       // per thread hides the ~2 us NVLink latency); fp32 wire loads rank by rank.
       constexpr int kPre = WIRE <= 16 ? kArMaxW : 1;
@@ -425,28 +420,40 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
         for (int r = 0; r < kPre; ++r)
           if (r < W) in[r] = granule_load_sys<WIRE>(p.data[r] + par * p.cap_bytes, e0);
       }
+      if (first && WIRE <= 16) {
+        unsigned acc = 0u;
+#pragma unroll
+        for (int r = 0; r < kPre; ++r)
+          if (r < W) acc ^= in[r].v[0].x;
+        asm volatile("" :: "r"(acc));                                   // all peer vectors have landed
+        stamp(p, 10);
+      }
       float s[16], cc[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) { s[i] = 0.f; cc[i] = 0.f; }
-      // the rank loop is deliberately NOT unrolled: the loads above are all in flight already, and 8 unrolled copies
-      // of decode + 16 casts (with their cold paths) made this kernel ~180 KB of SASS — at W = 8 the cold
-      // instruction-cache misses cost ~20 us per launch (measured: phase C of a 1 KB message 26 us -> see profiles/)
+      // the rank loop is not unrolled: the loads above are all in flight already, and 8 unrolled copies of decode +
+      // 16 casts (with their cold paths) only multiply the SASS (194 KB -> ~90 KB rolled) without adding parallelism
 #pragma unroll 1
       for (int r = 0; r < W; ++r) {
         {
           float v[16];
           if (WIRE <= 16) granule_decode<WIRE>(fmt, in[r % kPre], v);
           else granule_decode<WIRE>(fmt, granule_load_sys<WIRE>(p.data[r] + par * p.cap_bytes, e0), v);
+          // WIRE < 32: every operand is a member of the format -> hardware-assisted exact casts, 16 behind one guard
+          if (WIRE < 32) {
+            if (KAHAN) fold_kahan_members_n(fmt, s, cc, v);
+            else fold_plain_members_n(fmt, s, v);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            // WIRE < 32: every operand is a member of the format -> hardware-assisted exact casts
-            if (KAHAN) { if (WIRE < 32) fold_kahan_members(fmt, s[i], cc[i], v[i]); else fold_kahan(fmt, s[i], cc[i], v[i]); }
-            else if (p.ident) s[i] += v[i];
-            else if (WIRE < 32) fold_plain_members(fmt, s[i], v[i]);
-            else fold_plain(fmt, s[i], v[i]);
+            for (int i = 0; i < 16; ++i) {
+              if (KAHAN) fold_kahan(fmt, s[i], cc[i], v[i]);
+              else if (p.ident) s[i] += v[i];
+              else fold_plain(fmt, s[i], v[i]);
+            }
           }
         }
       }
+      if (first) stamp(p, 11);
       if (two_shot) {
         const Granule<WIRE> out = granule_encode<WIRE>(fmt, s);
         if (p.algo == ALGO_NVLS && p.mc_gather) {
@@ -462,6 +469,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
         for (int i = 0; i < 16; ++i) s[i] *= inv;
       }
       store16(p.grad + e0, s);
+      if (first) stamp(p, 12);
     }
   }
 

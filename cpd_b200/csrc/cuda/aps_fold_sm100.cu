@@ -94,19 +94,19 @@ aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__
       }
 #pragma unroll
       for (int k = 0; k < kVecPerThread; ++k) {
-        const float g[4] = {g4[k].x, g4[k].y, g4[k].z, g4[k].w};
+        float g[4] = {g4[k].x, g4[k].y, g4[k].z, g4[k].w};
+        if (use_aps) {
+          // the scaled casts make every value a member of the format, so every later cast acts on an exact sum of
+          // members: hardware-assisted exact path for the fp8-shaped formats, 4 casts per guard (wire_hw.cuh)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float v = g[j];
-          if (use_aps) {
-            // v becomes a member of the format, so every later cast acts on an exact sum of members:
-            // hardware-assisted exact path for the fp8-shaped formats (wire_hw.cuh)
-            v = fmt.q(v * sc);
-            if (KAHAN) fold_kahan_members(fmt, s[k][j], cc[KAHAN ? k : 0][j], v);
-            else fold_plain_members(fmt, s[k][j], v);
-          } else {
-            if (KAHAN) fold_kahan(fmt, s[k][j], cc[KAHAN ? k : 0][j], v);
-            else fold_plain(fmt, s[k][j], v);
+          for (int j = 0; j < 4; ++j) g[j] = fmt.q(g[j] * sc);
+          if (KAHAN) fold_kahan_members_n(fmt, s[k], cc[KAHAN ? k : 0], g);
+          else fold_plain_members_n(fmt, s[k], g);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (KAHAN) fold_kahan(fmt, s[k][j], cc[KAHAN ? k : 0][j], g[j]);
+            else fold_plain(fmt, s[k][j], g[j]);
           }
         }
       }

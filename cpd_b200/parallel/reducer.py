@@ -229,9 +229,11 @@ class GradReducer:
         workspace: amax, exponent exchange, pack, data barrier, fold, gather barrier (two-shot), unpack."""
         if self.local_ws is None or self.mode != "fused":
             return {}
-        t = self.local_ws[4 + 2 * MAX_TENSORS_PER_BUCKET:4 + 2 * MAX_TENSORS_PER_BUCKET + 16].cpu().view(torch.int64).tolist()
+        t = self.local_ws[4 + 2 * MAX_TENSORS_PER_BUCKET:4 + 2 * MAX_TENSORS_PER_BUCKET + 32].cpu().view(torch.int64).tolist()
         d = lambda a, b: round((t[b] - t[a]) / 1e3, 2) if t[a] and t[b] and t[b] >= t[a] else None  # noqa: E731
-        return {"A_amax+gridbar": d(0, 1), "exp_exchange": d(1, 2), "B_pack+gridbar": d(2, 3), "data_flags": d(3, 4), "C_fold": d(4, 5),
+        fine = {"C_first_granule": {"chunk+shift": d(4, 9), "peer_loads": d(9, 10), "decode+fold": d(10, 11), "encode+store": d(11, 12)}} \
+            if t[9] >= t[4] > 0 else {}
+        return {**fine, "A_amax+gridbar": d(0, 1), "exp_exchange": d(1, 2), "B_pack+gridbar": d(2, 3), "data_flags": d(3, 4), "C_fold": d(4, 5),
                 "gather_gridbar+flags": d(5, 6), "D_unpack": d(6, 7) if t[6] else None, "total": d(0, 7)}
 
     def guard_counters(self) -> dict:

@@ -196,6 +196,24 @@ def section_sweep(rank, world, res, max_bytes):
         fill(arena, rank, seed=3, scale_lo=-8, scale_hi=-2)
         iters = 200 if nbytes <= (1 << 20) else (40 if nbytes <= (1 << 26) else 8)
         row = dict(fp32_bytes=nbytes, elems=n)
+        # Every timed call reduces a FRESH copy of the gradients (a pool of iters + warm-up buffers, refilled before
+        # each variant): an in-place loop feeds each result back as the next input, the values grow ~W x per call,
+        # overflow to Inf/NaN after a few dozen calls at W = 8, and the kernels then time their exceptional paths.
+        # The pool is also larger than L2 for all but the smallest sizes, so the inputs are cold like a real step's.
+        K = iters + 3
+        orig = arena.grad_flat.clone()
+        pool = orig.unsqueeze(0).repeat(K, 1)
+        cursor = [0]
+
+        def refill():
+            pool.copy_(orig.unsqueeze(0).expand(K, -1))
+            cursor[0] = 0
+
+        def next_buf():
+            b = pool[cursor[0] % K]
+            cursor[0] += 1
+            return b
+
         for algo in ("raw", "oneshot", "twoshot", "nvls"):
             if algo == "oneshot" and nbytes > (1 << 26):
                 continue
@@ -204,26 +222,37 @@ def section_sweep(rank, world, res, max_bytes):
             red = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, algo=algo), mode="fused")
             if algo == "nvls" and not red.symm.has_multicast:
                 continue
-            ms = time_calls(red.reduce, iters)
+            refill()
+            ms = time_calls(lambda: red.reduce(next_buf()), iters)
             row[f"fused_{algo}_us"] = round(ms * 1e3, 2)
             row[f"fused_{algo}_phases_us"] = red.phase_times_us()
             row[f"fused_{algo}_busbw_fp32_GBps"] = round(nbytes / (ms * 1e-3) * 2 * (world - 1) / world / 1e9, 2)
             row[f"fused_{algo}_wire_GBps"] = round((n * red.wire / 8) / (ms * 1e-3) * 2 * (world - 1) / world / 1e9, 2)
+            row[f"fused_{algo}_finite_after"] = bool(torch.isfinite(pool).all())
             del red
-        redk = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, use_kahan=True, algo="auto"), mode="fused")
-        ms = time_calls(redk.reduce, iters)
-        row["fused_auto_kahan_us"] = round(ms * 1e3, 2)
-        del redk
-        g = arena.grad_flat
-        ms = time_calls(lambda: dist.all_reduce(g), iters)
+        for kname, kalgo in (("auto", "auto"),):
+            redk = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, use_kahan=True, algo=kalgo), mode="fused")
+            refill()
+            ms = time_calls(lambda: redk.reduce(next_buf()), iters)
+            row[f"fused_{kname}_kahan_us"] = round(ms * 1e3, 2)
+            redp = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, algo=kalgo), mode="fused")
+            refill()
+            ms = time_calls(lambda: redp.reduce(next_buf()), iters)
+            row[f"fused_{kname}_us"] = round(ms * 1e3, 2)
+            row[f"fused_{kname}_busbw_fp32_GBps"] = round(nbytes / (ms * 1e-3) * 2 * (world - 1) / world / 1e9, 2)
+            del redk, redp
+        refill()
+        ms = time_calls(lambda: dist.all_reduce(next_buf()), iters)
         row["nccl_fp32_allreduce_us"] = round(ms * 1e3, 2)
         row["nccl_fp32_busbw_GBps"] = round(nbytes / (ms * 1e-3) * 2 * (world - 1) / world / 1e9, 2)
         if nbytes <= (1 << 28):
-            gb = torch.empty(world, g.numel(), device=dev)
-            ms = time_calls(lambda: reference_algorithm(g, world, 4, 3, gb), max(iters // 4, 3))
+            gb = torch.empty(world, orig.numel(), device=dev)
+            refill()
+            ms = time_calls(lambda: reference_algorithm(next_buf(), world, 4, 3, gb), max(iters // 4, 3))
             row["reference_algo_us"] = round(ms * 1e3, 2)
             row["reference_algo_busbw_fp32_GBps"] = round(nbytes / (ms * 1e-3) * 2 * (world - 1) / world / 1e9, 2)
             del gb
+        del pool, orig
         rows.append(row)
         if rank == 0:
             print(json.dumps(row), flush=True)
