@@ -243,12 +243,14 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
       if (p.shifts_out && blockIdx.x == 0) p.shifts_out[t] = sh;
     }
     __syncthreads();
-    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
-      const Chunk ck = p.chunks[c];
+    // work item = a quarter chunk (1024 elements): one 4-element vector per thread, so every thread pays ONE peer
+    // round trip (a whole chunk per CTA meant 4 dependent ~2 us round trips while most of the 296 CTAs sat idle)
+    for (int w = blockIdx.x; w < 4 * p.n_chunks; w += gridDim.x) {
+      const Chunk ck = p.chunks[w >> 2];
       const int sh = s_shift[ck.tensor];
       const float sc = pow2i(sh), inv = pow2i(-sh);
-      // 4 elements per thread per step, all W peers' vectors requested before the first use
-      for (int v4 = threadIdx.x; v4 < (ck.len >> 2); v4 += kArThreads) {
+      // all W peers' vectors requested before the first use
+      for (int v4 = (w & 3) * kArThreads + threadIdx.x; v4 < (ck.len >> 2); v4 += 4 * kArThreads) {
         const long long e0 = ck.start + 4 * v4;
         uint4 in[kArMaxW];
 #pragma unroll

@@ -31,13 +31,19 @@ from .arena import ChunkTable, ModelArena
 _ALGO = {"auto": native.ALGO_AUTO, "oneshot": native.ALGO_ONESHOT, "twoshot": native.ALGO_TWOSHOT,
          "nvls": native.ALGO_NVLS, "raw": native.ALGO_ONESHOT_RAW}
 
-# packed bytes per bucket below which the one-shot variant (1 exchange fewer, W x the
-# fold work and (W-1)/1 x the NVLink reads) beats two-shot; tuned on 8xB200
+# Variant thresholds, from the 8 x B200 sweep with fresh (finite) gradients per call (profiles/allreduce_trip18_n8_*):
+#   fp32 payload      raw    one-shot   two-shot   NVLS    (us, (4,3) + APS, 8-bit wire)
+#   1 KB / 4 KB      21.3 / 21.9   29.1 / 29.3   35.6    35.2
+#   16 KB .. 1 MB    43.6 .. 51.5  30.4 .. 34.7  37.6 .. 39.9
+#   4 MB             78.6    48.4       46.5       45.7
+#   16 MB / 64 MB      -     103.6 / 293   69.7 / 167   67.8 / 166
+# -> raw (one flag round, fp32 on the wire) up to 1 K elements, packed one-shot up to 512 KB of wire codes, NVLS /
+#    two-shot above.  (The raw variant's jump between 4 KB and 16 KB is not understood yet - open item.)
 _FAULT_DELAY_RANK = int(os.environ.get("CPD_B200_FAULT_DELAY_RANK", "-1"))
 _FAULT_DELAY_CYCLES = float(os.environ.get("CPD_B200_FAULT_DELAY_CYCLES", "2e8"))
-ONESHOT_MAX_BYTES = 1024 * 1024     # measured on 8xB200: one-shot 58 us vs two-shot 72 us at 1 MB packed, 126 vs 99 us at 4 MB
+ONESHOT_MAX_BYTES = 512 * 1024
 MAX_TENSORS_PER_BUCKET = 1024
-RAW_MAX_ELEMS = 64 * 1024            # single-round raw-fp32 variant below 256 KB of gradients
+RAW_MAX_ELEMS = 1024
 
 
 class GradReducer:

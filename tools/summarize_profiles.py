@@ -104,7 +104,9 @@ def sweep_md(js, out_md):
         return
     lines = [f"# low-bit all-reduce sweep, {W} x B200 ((4,3) + APS, 8-bit wire)", "",
              "Device-timed (CUDA events, max over ranks).  busbw = fp32 payload / t * 2(W-1)/W (nccl-tests convention).  Roofline for the fused kernel = slower of",
-             "(wire bytes that must cross NVLink per GPU / 770 GB/s measured) and (local HBM traffic ~ 13 B/element / measured copy bandwidth).", "",
+             "(wire bytes that must cross NVLink per GPU / 770 GB/s measured) and (local HBM traffic ~ 13 B/element / measured copy bandwidth).",
+             ("Every timed call reduces a fresh copy of the gradients (finite values)." if any(k.endswith("finite_after") for r in rows for k in r) else
+              "NOTE: taken with an in-place timing loop - the values overflow to Inf/NaN after a few dozen calls at W = 8, so the fused columns time the exceptional path (pessimistic); superseded by the later sweeps."), "",
              "| fp32 bytes | fused one-shot (best of packed / raw) us | fused two-shot us | fused NVLS us | fused Kahan us | NCCL fp32 all_reduce us | reference algorithm us | best fused busbw GB/s | NCCL busbw GB/s | reference busbw GB/s | fused roofline us | fused / roofline |",
              "|---|---|---|---|---|---|---|---|---|---|---|---|"]
     try:
@@ -133,7 +135,8 @@ def main():
     for p in glob.glob(os.path.join(GO, "trip*", "microbench.json")) + glob.glob(os.path.join(GO, "trip*", "bench_gemm.json")):
         if os.path.getsize(p) > 10:
             shutil.copy(p, os.path.join(PR, os.path.basename(os.path.dirname(p)) + "_" + os.path.basename(p)))
-    for p in glob.glob(os.path.join(GO, "trip*", "sweep.json")) + glob.glob(os.path.join(GO, "trip*", "check.json")):
+    for p in glob.glob(os.path.join(GO, "trip*", "sweep.json")) + glob.glob(os.path.join(GO, "trip*", "check.json")) + \
+            glob.glob(os.path.join(GO, "trip*", "check_sweep.json")) + glob.glob(os.path.join(GO, "trip*", "fake8.json")):
         tag = os.path.basename(os.path.dirname(p))
         shutil.copy(p, os.path.join(PR, f"allreduce_{tag}_{os.path.basename(p)}"))
         if p.endswith("sweep.json"):
