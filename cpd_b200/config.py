@@ -66,3 +66,5 @@ def add_precision_args(p: argparse.ArgumentParser, grad_exp: int = 5, grad_man: 
     p.add_argument("--wire", choices=["auto", "8", "16", "32"], default="auto")
     p.add_argument("--bucket_mb", "--bucket-mb", dest="bucket_mb", type=float, default=0.0)
     p.add_argument("--overlap", action="store_true")
+    p.add_argument("--profile_trace", "--profile-trace", dest="profile_trace", default="",
+                   help="write a torch.profiler chrome trace of a few steady-state steps to this path (rank 0)")

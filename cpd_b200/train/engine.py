@@ -186,6 +186,23 @@ class TrainEngine:
     def check(self) -> None:
         self.reducer.check_status()
 
+    def comm_stats(self) -> dict:
+        """Observability of the gradient path for the JSONL log: APS shift histogram of the last step,
+        non-finite / all-zero tensor counters and, for the fused all-reduce, the device-stamped duration of the last launch.
+        Host-synchronising (reads small device buffers) - call it at log points only."""
+        out = {}
+        if self.cfg.use_aps and getattr(self.reducer, "shifts", None):
+            sh = torch.cat([s.flatten() for s in self.reducer.shifts]).cpu()
+            if sh.numel():
+                vals, counts = torch.unique(sh, return_counts=True)
+                out["aps_shift_min"], out["aps_shift_max"] = int(sh.min()), int(sh.max())
+                out["aps_shift_hist"] = {int(v): int(c) for v, c in zip(vals.tolist(), counts.tolist())}
+        out.update(self.reducer.guard_counters())
+        ph = self.reducer.phase_times_us()
+        if ph.get("total") is not None:
+            out["comm_us_last_launch"] = ph["total"]
+        return out
+
     def state_dict(self) -> dict:
         return {"model": {k: v.detach().cpu() for k, v in self.model.state_dict().items()},
                 "optimizer": self.optimizer.state_dict(), "step": self.step_count, "precision": self.cfg.to_dict()}

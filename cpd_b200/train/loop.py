@@ -8,6 +8,7 @@ as the max over ranks; logging reductions run every ``print_freq`` steps instead
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from dataclasses import dataclass
 from typing import Callable, Iterable, Optional
@@ -15,7 +16,7 @@ from typing import Callable, Iterable, Optional
 import torch
 import torch.distributed as dist
 
-from ..utils import AverageMeter, DeviceTimer, JsonlLogger, ScalarWriter, accuracy, find_latest, load_state, make_state, save_checkpoint
+from ..utils import AverageMeter, DeviceTimer, JsonlLogger, ScalarWriter, accuracy, find_latest, load_state, make_state, save_checkpoint, trace
 from .engine import TrainEngine
 
 
@@ -30,6 +31,9 @@ class LoopConfig:
     tensorboard_dir: Optional[str] = None
     resume: Optional[str] = None          # checkpoint path or "auto"
     arch: str = "model"
+    profile_trace: Optional[str] = None   # chrome trace (torch.profiler) of `profile_steps` steps starting at `profile_start`
+    profile_start: int = 10
+    profile_steps: int = 3
 
 
 def validate(engine: TrainEngine, val_batches: Iterable, rank: int, world: int):
@@ -64,22 +68,30 @@ def run(engine: TrainEngine, train_batches: Iterable, cfg: LoopConfig, val_batch
     imgs_per_step = engine.batch_size * engine.E * world
     timer.start()
     window, step = 0, start_iter
+    prof_stack = contextlib.ExitStack()
     for x, y in train_batches:
         if step >= cfg.max_iter:
             break
         step += 1
+        if cfg.profile_trace and step == start_iter + cfg.profile_start:
+            prof_stack.enter_context(trace(cfg.profile_trace, rank))
         lr = cfg.lr_fn(step)
         engine.train_step(x, y, lr=lr)
+        if cfg.profile_trace and step == start_iter + cfg.profile_start + cfg.profile_steps - 1:
+            if engine.is_cuda:
+                torch.cuda.synchronize()
+            prof_stack.close()
         window += 1
         if step == 1 or step % cfg.print_freq == 0:
             gl = engine.global_loss()
             losses.update(gl)
             ms = timer.stop_ms()
             ips = imgs_per_step * window / (ms / 1e3)
+            stats = engine.comm_stats()
             if rank == 0:
                 print(f"Iter: [{step}/{cfg.max_iter}]\tLoss {gl:.4f} ({losses.avg:.4f})\tLR {lr:.4f}\t"
                       f"{ips:,.0f} img/s (device-timed, max over ranks)", flush=True)
-                jl.log(step=step, loss=gl, lr=lr, images_per_sec=ips, ms_per_step=ms / window)
+                jl.log(step=step, loss=gl, lr=lr, images_per_sec=ips, ms_per_step=ms / window, **stats)
                 if tb:
                     tb.add_scalar("loss_train", losses.avg, step)
                     tb.add_scalar("lr", lr, step)
@@ -102,6 +114,7 @@ def run(engine: TrainEngine, train_batches: Iterable, cfg: LoopConfig, val_batch
                                            extra={"arch": cfg.arch}), os.path.join(cfg.save_path, f"ckpt_{step}.pth"), is_best, rank)
             timer.start()
             window = 0
+    prof_stack.close()
     jl.close()
     if tb:
         tb.close()

@@ -62,7 +62,7 @@ def main():
     def val_batches():
         return torch.utils.data.DataLoader(val_ds, batch_size=args.batch_size, shuffle=False, num_workers=0, pin_memory=True,
                                            sampler=DistributedSampler(val_ds, world_size=world, rank=rank, round_up=False, shuffle=False))
-    lc = LoopConfig(max_iter=max_iter, lr_fn=sched, print_freq=args.print_freq, val_freq=args.val_freq, save_path=args.save_path,
+    lc = LoopConfig(max_iter=max_iter, lr_fn=sched, print_freq=args.print_freq, val_freq=args.val_freq, save_path=args.save_path, profile_trace=args.profile_trace or None,
                     log_jsonl=os.path.join(args.save_path, "train.jsonl"), tensorboard_dir=os.path.join(args.save_path, "events"),
                     resume=(args.load_path or None), arch=args.arch)
     if args.evaluate:

@@ -73,7 +73,7 @@ def main():
                                            sampler=DistributedSampler(val_ds, world_size=world, rank=rank, round_up=False, shuffle=False))
 
     save_dir = os.path.dirname(os.path.abspath(args.checkpoint_format)) or "."
-    lc = LoopConfig(max_iter=args.max_iter or it_per_epoch * args.epochs, lr_fn=sched, print_freq=50, val_freq=it_per_epoch,
+    lc = LoopConfig(max_iter=args.max_iter or it_per_epoch * args.epochs, lr_fn=sched, print_freq=50, val_freq=it_per_epoch, profile_trace=args.profile_trace or None,
                     save_path=save_dir, log_jsonl=os.path.join(args.log_dir, "train.jsonl"), resume="auto", arch="resnet50")
     run(engine, batches(), lc, val_batches)
 

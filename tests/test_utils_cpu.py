@@ -193,3 +193,36 @@ def test_graphnet_from_nested_dict_matches_builtin_davidnet():
     x = torch.randn(2, 3, 32, 32)
     g.eval(); ref.eval()
     assert torch.allclose(g(x), ref(x), atol=1e-5)
+
+
+def test_comm_stats_and_profiler_trace(tmp_path):
+    """Observability: APS shift histogram + guard counters for the JSONL log, chrome trace export."""
+    import json
+    from cpd_b200.train import TrainEngine
+    from cpd_b200.train.loop import LoopConfig, run
+    from cpd_b200.utils import trace, nvtx_range
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(48, 16), torch.nn.ReLU(), torch.nn.Linear(16, 10))
+    eng = TrainEngine(m, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True), batch_size=4, input_shape=(3, 4, 4), lr=0.05,
+                      use_lars=False, cuda_graph=False)
+    x, y = torch.randn(4, 3, 4, 4), torch.randint(0, 10, (4,))
+    eng.train_step(x, y)
+    st = eng.comm_stats()
+    assert sum(st["aps_shift_hist"].values()) == 4 and st["aps_shift_min"] <= st["aps_shift_max"]      # 4 parameter tensors
+    log = str(tmp_path / "log.jsonl")
+    tr = str(tmp_path / "trace.json")
+    run(eng, [(x, y)] * 6, LoopConfig(max_iter=6, lr_fn=lambda s: 0.05, print_freq=2, log_jsonl=log, profile_trace=tr, profile_start=2, profile_steps=2))
+    rows = [json.loads(line) for line in open(log)]
+    assert rows and "aps_shift_hist" in rows[-1] and "images_per_sec" in rows[-1]
+    assert os.path.getsize(tr) > 100 and "traceEvents" in open(tr).read(4096)
+    with trace(None) as p, nvtx_range("noop"):
+        assert p is None
+
+
+def test_committed_profiles_hold_the_perf_floors():
+    """The evidence under profiles/ must keep satisfying tools/check_perf_floors.py (SURVEY §4 'Perf regression')."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_perf_floors.py")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-3000:]
