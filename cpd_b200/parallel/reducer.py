@@ -19,6 +19,7 @@ reduction overlaps the rest of backward (``overlap=True``).
 from __future__ import annotations
 
 import os
+import warnings
 from typing import List, Optional
 
 import torch
@@ -70,6 +71,7 @@ class GradReducer:
         if not (cfg.use_aps or cfg.prequantize):
             self.wire = 32          # raw fp32 gradients travel: the first cast happens inside the fold
 
+        explicit_mode = mode is not None
         if mode is None:
             if self.world == 1:
                 mode = "local"
@@ -101,8 +103,17 @@ class GradReducer:
             cap = max(self.max_numel * (self.wire // 8), min(self.max_numel, RAW_MAX_ELEMS) * 4)
             if cfg.algo == "raw":
                 cap = self.max_numel * 4
-            self.symm = SymmetricWorkspace(cap, MAX_TENSORS_PER_BUCKET, group=group)
-        elif self.mode == "gather" and self.world > 1:
+            try:
+                self.symm = SymmetricWorkspace(cap, MAX_TENSORS_PER_BUCKET, group=group)
+            except RuntimeError as err:
+                # no peer-memory backend (no P2P, > 8 ranks, ...): every rank fails together (the bring-up agrees on
+                # each step collectively), so an auto-selected fused mode degrades to the reference algorithm on NCCL
+                if explicit_mode:
+                    raise
+                if self.rank == 0:
+                    warnings.warn(f"cpd_b200: fused all-reduce unavailable ({err}); falling back to all_gather + fold on NCCL")
+                self.mode = "gather"
+        if self.mode == "gather" and self.world > 1:
             self._gather_buf = torch.empty(self.world, self.max_numel, dtype=torch.float32, device=self.device)
 
         # overlap machinery
