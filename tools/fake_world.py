@@ -17,6 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 from cpd_b200 import PrecisionConfig, _C  # noqa: E402
+from cpd_b200.ops import native  # noqa: E402
 from cpd_b200.parallel import GradReducer  # noqa: E402
 from cpd_b200.parallel.symm import FLAG_WORDS  # noqa: E402
 from multigpu_check import FakeArena, fill  # noqa: E402
@@ -44,18 +45,15 @@ def fake(red):
     base = s.ptrs[0]
     # flags of the imaginary peers: far ahead of any epoch this run reaches; mailbox: -inf exponents
     from cuda.bindings import runtime as rt
-    host_mb = torch.full(((s.off_flags - s.off_mailbox) // 4,), float("-inf"), dtype=torch.float32, device=dev)
-    host_fl = torch.full((FLAG_WORDS,), 1 << 30, dtype=torch.int32, device=dev)
+    mb_init = torch.full(((s.off_flags - s.off_mailbox) // 4,), float("-inf"), dtype=torch.float32, device=dev)
+    flag_init = torch.full((FLAG_WORDS,), 1 << 30, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
-    for off, d in ((s.off_mailbox, host_mb), (s.off_flags, host_fl)):
+    for off, d in ((s.off_mailbox, mb_init), (s.off_flags, flag_init)):
         err, = rt.cudaMemcpy(base + off, d.data_ptr(), d.numel() * 4, rt.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
         assert int(err) == 0, err
     torch.cuda.synchronize()
     s.buffers = _C.CommBuffers(0, W, [base + s.off_data] * W, [base + s.off_gather] * W,
                                [base + s.off_mailbox] * W, [base + s.off_flags] * W, 0, s.cap_bytes, s.max_tensors)
-
-
-from cpd_b200.ops import native  # noqa: E402
 
 
 def check():
