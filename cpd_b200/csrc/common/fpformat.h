@@ -196,6 +196,33 @@ struct FormatT {
     }
     return q_slow(x);
   }
+  // Same cast with the target-SUBNORMAL range (and zeros) handled inline as well.  APS maps the largest |g| of
+  // a tensor to the top of the format, so with real gradients (several decades of dynamic range) a large share
+  // of the scaled values land below the smallest normal of a 4- or 5-bit-exponent format: in q() every warp
+  // then takes the out-of-line call for almost every element.  Here they cost ~12 straight-line integer
+  // instructions (truncating shift = quirk B, RNE at the same bit position, exact rebuild through the 2^23
+  // magic constant: no int->float conversion).  Only Inf/NaN/overflow still leave the inlined code.
+  static CPD_HD float q_wide(float x) {
+    const uint32_t u = f2u(x);
+    const uint32_t a = u & 0x7FFFFFFFu;
+    const uint32_t E = a >> 23;
+    if (E - uint32_t(lo) < uint32_t(hi - lo)) {            // target-normal
+      if (drop == 0) return x;
+      const uint32_t lsb = drop == 23 ? 1u : ((a >> drop) & 1u);
+      const uint32_t r = (a + half_m1 + lsb) & keep;
+      return u2f((u & 0x80000000u) | r);
+    }
+    if (E < uint32_t(lo)) {
+      if (E == 0u) return u2f(a == 0u ? u : 0u);           // +-0 passes through, fp32 denormals become +0
+      uint32_t s = uint32_t(lo) - E;                        // >= 1
+      if (s > 31u) s = 31u;
+      uint32_t M = ((a & 0x7FFFFFu) | 0x800000u) >> s;      // < 2^23
+      if (drop > 0) M = (M + half_m1 + ((M >> drop) & 1u)) & keep;     // <= 2^23
+      const float r = (u2f(0x4B000000u + M) - 8388608.0f) * u2f(sub_se > 0 ? (uint32_t(sub_se) << 23) : 0u);
+      return u2f(f2u(r) | (u & 0x80000000u));
+    }
+    return q_slow(x);
+  }
 };
 
 // ---- accumulation steps ----------------------------------------------------
@@ -298,6 +325,7 @@ template <int E_BITS, int M_BITS>
 struct FmtT {
   static constexpr int kExp = E_BITS, kMan = M_BITS;
   CPD_HD float q(float x) const { return FormatT<E_BITS, M_BITS>::q(x); }
+  CPD_HD float q_wide(float x) const { return FormatT<E_BITS, M_BITS>::q_wide(x); }   // subnormal range inline too
   CPD_HD uint32_t pack(float v) const { return wire_pack(v, E_BITS, wire_man(M_BITS)); }
   CPD_HD float unpack(uint32_t c) const { return wire_unpack(c, E_BITS, wire_man(M_BITS)); }
   CPD_HD int exp_bits() const { return E_BITS; }
@@ -310,6 +338,7 @@ static CPD_COLD float wire_unpack_rt(uint32_t c, int e, int m) { return wire_unp
 struct FmtR {
   Format f;
   CPD_HD float q(float x) const { return quantize_rt(x, f); }
+  CPD_HD float q_wide(float x) const { return quantize_rt(x, f); }
   CPD_HD uint32_t pack(float v) const { return wire_pack_rt(v, f.exp_bits, wire_man(f.man_bits)); }
   CPD_HD float unpack(uint32_t c) const { return wire_unpack_rt(c, f.exp_bits, wire_man(f.man_bits)); }
   CPD_HD int exp_bits() const { return f.exp_bits; }

@@ -264,7 +264,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
             float v[4] = {__uint_as_float(in[r].x) * sc, __uint_as_float(in[r].y) * sc, __uint_as_float(in[r].z) * sc,
                           __uint_as_float(in[r].w) * sc};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = fmt.q(v[i]);
+            for (int i = 0; i < 4; ++i) v[i] = fmt.q_wide(v[i]);
             if (KAHAN) fold_kahan_members_n(fmt, s4, c4, v);
             else fold_plain_members_n(fmt, s4, v);
           }
@@ -383,7 +383,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
       const float sc = p.use_aps ? pow2i(s_shift[ck0.tensor]) : 1.f;
       if (p.use_aps || p.prequant) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x0[i] = fmt.q(x0[i] * sc);
+        for (int i = 0; i < 16; ++i) x0[i] = fmt.q_wide(x0[i] * sc);
       }
       granule_store<WIRE>(my_data, e0, granule_encode<WIRE>(fmt, x0), false);
     }
@@ -391,7 +391,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
       const float sc = p.use_aps ? pow2i(s_shift[ck1.tensor]) : 1.f;
       if (p.use_aps || p.prequant) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x1[i] = fmt.q(x1[i] * sc);
+        for (int i = 0; i < 16; ++i) x1[i] = fmt.q_wide(x1[i] * sc);
       }
       granule_store<WIRE>(my_data, e1, granule_encode<WIRE>(fmt, x1), false);
     }

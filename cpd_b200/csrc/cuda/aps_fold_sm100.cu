@@ -99,7 +99,7 @@ aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__
           // the scaled casts make every value a member of the format, so every later cast acts on an exact sum of
           // members: hardware-assisted exact path for the fp8-shaped formats, 4 casts per guard (wire_hw.cuh)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) g[j] = fmt.q(g[j] * sc);
+          for (int j = 0; j < 4; ++j) g[j] = fmt.q_wide(g[j] * sc);
           if (KAHAN) fold_kahan_members_n(fmt, s[k], cc[KAHAN ? k : 0], g);
           else fold_plain_members_n(fmt, s[k], g);
         } else {

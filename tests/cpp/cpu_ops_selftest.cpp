@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../cpd_b200/csrc/api.h"
+#include "../../cpd_b200/csrc/common/fpformat.h"
 
 static int failures = 0;
 #define CHECK(cond, ...)                                                     \
@@ -38,8 +39,44 @@ static std::vector<float> adversarial(std::mt19937& rng, size_t n) {
   return v;
 }
 
+// compile-time casts (the ones the CUDA kernels inline) == the generic reference cast, on every upper-half bit
+// pattern x a set of lower halves that exercise ties, just-above/below ties and all-ones mantissas
+template <int E, int M>
+static void check_static_casts() {
+  const cpd::Format f = cpd::make_format(E, M, cpd::ROUND_REF);
+  const uint32_t lows[] = {0x0000u, 0x0001u, 0x7FFFu, 0x8000u, 0x8001u, 0xFFFFu, 0x1234u, 0xFFF0u};
+  long bad = 0;
+  for (uint32_t hi = 0; hi < 65536u; ++hi)
+    for (uint32_t lo : lows) {
+      const float x = from_bits((hi << 16) | lo);
+      const float want = cpd::quantize_ref(x, f);
+      const float a = cpd::FormatT<E, M>::q(x), b = cpd::FormatT<E, M>::q_wide(x);
+      if (!same(a, want) || !same(b, want)) {
+        if (++bad <= 3) std::fprintf(stderr, "FAIL static cast (%d,%d) x=%a: q=%a q_wide=%a want=%a\n", E, M, x, a, b, want);
+      }
+    }
+  // random mantissas over the exponents around and below the smallest normal (the inline subnormal path of q_wide)
+  std::mt19937 rng(E * 100 + M);
+  const int lo_e = cpd::FormatT<E, M>::lo;
+  for (int i = 0; i < 2000000; ++i) {
+    const uint32_t r = rng();
+    int e = lo_e + 2 - int(r % 30u);
+    if (e < 1) e = 1;
+    if (e > 254) e = 254;
+    const float x = from_bits((rng() & 0x807FFFFFu) | (uint32_t(e) << 23));
+    const float want = cpd::quantize_ref(x, f);
+    const float b = cpd::FormatT<E, M>::q_wide(x);
+    if (!same(b, want) && ++bad <= 3) std::fprintf(stderr, "FAIL q_wide (%d,%d) x=%a: %a want %a\n", E, M, x, b, want);
+  }
+  if (bad) failures += (int)bad;
+}
+
 int main() {
   std::mt19937 rng(1234);
+  check_static_casts<4, 3>(); check_static_casts<5, 2>(); check_static_casts<5, 10>(); check_static_casts<8, 7>();
+  check_static_casts<8, 23>(); check_static_casts<3, 0>(); check_static_casts<2, 1>(); check_static_casts<8, 0>();
+  check_static_casts<1, 1>(); check_static_casts<6, 9>(); check_static_casts<3, 4>(); check_static_casts<8, 22>();
+  check_static_casts<7, 16>(); check_static_casts<5, 23>();
   const int fmts[][2] = {{4, 3}, {5, 2}, {3, 0}, {5, 10}, {8, 7}, {8, 23}, {2, 1}, {8, 0}, {1, 1}, {6, 9}, {3, 4}, {8, 22}};
 
   // ---- cast: idempotent, sign-symmetric, monotone on finite inputs, identity for (8,23); zero-size is legal ----
