@@ -250,6 +250,10 @@ class GradReducer:
         d = lambda a, b: round((t[b] - t[a]) / 1e3, 2) if t[a] and t[b] and t[b] >= t[a] else None  # noqa: E731
         fine = {"C_first_granule": {"chunk+shift": d(4, 9), "peer_loads": d(9, 10), "decode+fold": d(10, 11), "encode+store": d(11, 12)}} \
             if t[9] >= t[4] > 0 else {}
+        if t[4] and t[2] < t[0]:                    # raw variant: no exponent / pack stamps in this launch (older ones are stale)
+            return {"A_amax+gridbar": d(0, 1), "push+flags": d(1, 4), "fold": d(4, 7), "total": d(0, 7),
+                    "exp_exchange": None, "B_pack+gridbar": None, "data_flags": None, "C_fold": None,
+                    "gather_gridbar+flags": None, "D_unpack": None}
         return {**fine, "A_amax+gridbar": d(0, 1), "exp_exchange": d(1, 2), "B_pack+gridbar": d(2, 3), "data_flags": d(3, 4), "C_fold": d(4, 5),
                 "gather_gridbar+flags": d(5, 6), "D_unpack": d(6, 7) if t[6] else None, "total": d(0, 7)}
 

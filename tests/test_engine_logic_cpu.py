@@ -63,3 +63,28 @@ def test_reducer_wire_and_mode_selection():
     arena.grad_flat.copy_(before)
     r.reduce()
     assert torch.equal(arena.grad_flat, after_one)
+
+
+def test_variant_selection_follows_the_measured_thresholds():
+    """algo_for(): raw (one flag round) for tiny APS buckets, packed one-shot up to ONESHOT_MAX_BYTES of wire codes,
+    NVLS / two-shot above; 2 ranks always one-shot; a forced algo is honoured."""
+    from types import SimpleNamespace
+    from cpd_b200.ops import native
+    from cpd_b200.parallel import reducer as R
+    arena = ModelArena(list(_net().parameters()))
+    r = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True))
+    bucket = lambda n: SimpleNamespace(numel=n)                                     # noqa: E731
+    r.world, r.symm = 8, SimpleNamespace(has_multicast=True)
+    assert r.algo_for(bucket(R.RAW_MAX_ELEMS)) == native.ALGO_ONESHOT_RAW
+    assert r.algo_for(bucket(R.RAW_MAX_ELEMS + 16)) == native.ALGO_ONESHOT
+    assert r.algo_for(bucket(R.ONESHOT_MAX_BYTES)) == native.ALGO_ONESHOT            # 8-bit wire: bytes == elements
+    assert r.algo_for(bucket(R.ONESHOT_MAX_BYTES + 16)) == native.ALGO_NVLS
+    r.symm = SimpleNamespace(has_multicast=False)
+    assert r.algo_for(bucket(1 << 24)) == native.ALGO_TWOSHOT
+    r.world = 2
+    assert r.algo_for(bucket(1 << 24)) == native.ALGO_ONESHOT
+    r.world = 8
+    r.cfg = PrecisionConfig(grad_exp=4, grad_man=3, use_aps=False, prequantize=True)
+    assert r.algo_for(bucket(64)) == native.ALGO_ONESHOT                            # raw variant needs APS exponents
+    r.cfg = PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, algo="twoshot")
+    assert r.algo_for(bucket(64)) == native.ALGO_TWOSHOT
