@@ -1,4 +1,6 @@
 """CUDA kernels == C++ CPU ops bit for bit (SURVEY §4 'Unit, GPU'); run on the B200 via gpurun."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -297,3 +299,20 @@ def test_quant_conv_tile_mode_first_layer_k27():
     assert (y - ref).abs().max() / ref.abs().max() < 3e-2
     y.sum().backward()
     assert torch.isfinite(qc.weight.grad).all() and torch.isfinite(x.grad).all()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [8, 4])
+def test_fused_allreduce_fake_world_matches_cpu_fold(world):
+    """The cross-GPU kernel on ONE GPU: it is told world_size = W while every peer pointer aliases local memory
+    (tools/fake_world.py), so the raw and packed one-shot variants run their full W-rank instruction stream —
+    amax, exponent mailboxes, scale + cast + pack, W-rank decode + fold (plain and Kahan), unscale — and the result
+    must equal the pure-software CPU fold of W copies bit for bit, incl. tensors with NaN / Inf / zeros."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29700 + world + os.getpid() % 200))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fake_world.py"), "--check-only", "--no-denormals", "--world", str(world)],
+                       capture_output=True, text=True, timeout=280, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "mismatching cases: none" in r.stdout, r.stdout[-3000:]

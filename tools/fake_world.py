@@ -29,6 +29,7 @@ ap.add_argument("--out", default="")
 ap.add_argument("--check-only", action="store_true")
 ap.add_argument("--seed", type=int, default=0)
 ap.add_argument("--gpu-denormals", action="store_true")
+ap.add_argument("--no-denormals", action="store_true", help="leave the fp32-denormal tensor out of the check")
 args = ap.parse_args()
 
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -73,7 +74,9 @@ def check():
                 g[off[3]:off[3] + 16] = 0.0
                 g[off[4] + 11] = -float("inf")
                 gen = torch.Generator().manual_seed(100 * e + m + (7 if kahan else 0) + (3 if algo == "raw" else 0) + args.seed)
-                if args.gpu_denormals:
+                if args.no_denormals:
+                    g[off[5]:off[5] + 300] = torch.randn(300, generator=gen).to(dev) * 3e-5
+                elif args.gpu_denormals:
                     g[off[5]:off[5] + 300] = torch.randn(300, device=dev) * 1e-41
                 else:
                     g[off[5]:off[5] + 300] = (torch.randn(300, generator=gen) * 1e-41).to(dev)          # fp32 denormals
