@@ -320,6 +320,22 @@ CPD_HD float wire_unpack(uint32_t code, const int E_BITS, const int M_BITS) {
   return u2f(f2u(scaled) | s);
 }
 
+// x with the low significand bits cleared that the reference's truncating subnormal shift discards (quirk B) and
+// fp32 denormals turned into +0: an IEEE round-to-nearest-even convert of the result — e.g. Blackwell's
+// F2FP.SATFINITE.E4M3/E5M2 — then reproduces the reference cast exactly for every finite |x| below the overflow
+// band (the reference rounds the truncated significand at the same bit position; after the masking the hardware sees
+// the same bits).  6 integer instructions, no control flow.  Proven against quantize_ref() in tests/cpp.
+template <int E_BITS, int M_BITS>
+CPD_HD float pretruncate(float x) {
+  constexpr uint32_t lo = uint32_t(FormatT<E_BITS, M_BITS>::lo);
+  const uint32_t u = f2u(x);
+  const uint32_t E = (u >> 23) & 0xFFu;
+  uint32_t s = lo > E ? lo - E : 0u;                    // bits the reference shifts out (0 for target-normal inputs)
+  if (s > 23u) s = 23u;                                 // whole mantissa gone: +-2^(E-127) rounds to +-0 like the reference's M = 0
+  const uint32_t t = u & (0xFFFFFFFFu << s);
+  return u2f((E == 0u && (u & 0x7FFFFFu) != 0u) ? 0u : t);
+}
+
 // Format policies used by templated kernels: q() = cast, pack()/unpack() = wire codec.
 template <int E_BITS, int M_BITS>
 struct FmtT {

@@ -50,6 +50,7 @@ struct ArParams {
   const Chunk* chunks;
   int n_chunks, T;
   int use_aps, algo, prequant, ident;
+  int pack_hw;           // opt-in (algo bit 8): hardware scale+cast+pack of phase B for the fp8-shaped formats
   unsigned* ws;          // [0],[1] grid barrier; [2] epoch; [3] status; [4..4+2*max_tensors) amax[2][max_tensors]
   int* shifts_out;
   unsigned long long timeout;
@@ -178,6 +179,23 @@ __device__ __forceinline__ void stamp(const ArParams& p, int i) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     reinterpret_cast<unsigned long long*>(p.ws + 4 + 2 * p.max_tensors)[i] = t;
   }
+}
+
+// phase B for one granule: x -> Q(x * sc) -> wire codes in the rank's own buffer
+template <int WIRE, class F>
+__device__ __forceinline__ void pack_granule(const ArParams& p, const F& fmt, float (&x)[16], float sc, unsigned char* my_data, long long e0) {
+  if (WIRE == 8 && p.pack_hw && (p.use_aps || p.prequant)) {
+    unsigned w[4];
+    if (FoldOps<F>::pack16_scaled(fmt, x, sc, w)) {
+      st_u4(my_data + e0, make_uint4(w[0], w[1], w[2], w[3]));
+      return;
+    }
+  }
+  if (p.use_aps || p.prequant) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = fmt.q_wide(x[i] * sc);
+  }
+  granule_store<WIRE>(my_data, e0, granule_encode<WIRE>(fmt, x), false);
 }
 
 template <class F, int WIRE, bool KAHAN>
@@ -379,22 +397,8 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
     float x0[16], x1[16];
     if (a0) load16(p.grad + e0, x0);
     if (a1) load16(p.grad + e1, x1);
-    if (a0) {
-      const float sc = p.use_aps ? pow2i(s_shift[ck0.tensor]) : 1.f;
-      if (p.use_aps || p.prequant) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x0[i] = fmt.q_wide(x0[i] * sc);
-      }
-      granule_store<WIRE>(my_data, e0, granule_encode<WIRE>(fmt, x0), false);
-    }
-    if (a1) {
-      const float sc = p.use_aps ? pow2i(s_shift[ck1.tensor]) : 1.f;
-      if (p.use_aps || p.prequant) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x1[i] = fmt.q_wide(x1[i] * sc);
-      }
-      granule_store<WIRE>(my_data, e1, granule_encode<WIRE>(fmt, x1), false);
-    }
+    if (a0) pack_granule<WIRE>(p, fmt, x0, p.use_aps ? pow2i(s_shift[ck0.tensor]) : 1.f, my_data, e0);
+    if (a1) pack_granule<WIRE>(p, fmt, x1, p.use_aps ? pow2i(s_shift[ck1.tensor]) : 1.f, my_data, e1);
   }
   grid_barrier(bar);
   stamp(p, 3);
@@ -537,7 +541,8 @@ void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunk
   p.cap_bytes = (long long)cb.cap_bytes;
   p.max_tensors = cb.max_tensors;
   p.grad = grad; p.chunks = chunks; p.n_chunks = n_chunks; p.T = T;
-  p.use_aps = use_aps; p.algo = algo; p.prequant = prequant;
+  p.use_aps = use_aps; p.algo = algo & 0xFF; p.prequant = prequant;
+  p.pack_hw = (algo >> 8) & 1;
   p.ident = (e == 8 && m == 23 && !kahan) ? 1 : 0;
   p.ws = local_ws; p.shifts_out = shifts_out; p.timeout = timeout_cycles;
   if (p.algo == ALGO_NVLS && !cb.mc_gather) p.algo = ALGO_TWOSHOT;

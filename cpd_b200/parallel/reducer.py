@@ -40,6 +40,9 @@ _ALGO = {"auto": native.ALGO_AUTO, "oneshot": native.ALGO_ONESHOT, "twoshot": na
 #   16 MB / 64 MB      -     103.6 / 293   69.7 / 167   67.8 / 166
 # -> raw (one flag round, fp32 on the wire) up to 1 K elements, packed one-shot up to 512 KB of wire codes, NVLS /
 #    two-shot above.  (The raw variant's jump between 4 KB and 16 KB is not understood yet - open item.)
+# opt-in: phase B of the fused kernel packs (4,3)/(5,2) granules with the hardware convert after pretruncate()
+# (algorithm proven against the reference cast on the CPU, tests/cpp; not yet measured on the GPU -> off by default)
+_PACK_HW = 0x100 if os.environ.get("CPD_B200_PACK_HW", "0") == "1" else 0
 _FAULT_DELAY_RANK = int(os.environ.get("CPD_B200_FAULT_DELAY_RANK", "-1"))
 _FAULT_DELAY_CYCLES = float(os.environ.get("CPD_B200_FAULT_DELAY_CYCLES", "2e8"))
 ONESHOT_MAX_BYTES = 512 * 1024
@@ -155,7 +158,7 @@ class GradReducer:
         elif self.mode == "fused":
             native._C.allreduce_fused_cuda(
                 self.symm.buffers, g.data_ptr(), b.numel, b.chunks.data_ptr(), b.n_chunks, b.T, e, m,
-                bool(cfg.use_aps), bool(cfg.use_kahan), self.algo_for(b), bool(cfg.prequantize), self.wire,
+                bool(cfg.use_aps), bool(cfg.use_kahan), self.algo_for(b) | _PACK_HW, bool(cfg.prequantize), self.wire,
                 self.local_ws.data_ptr(), self.shifts[i].data_ptr(), int(cfg.comm_ctas), self.timeout_cycles,
                 torch.cuda.current_stream(self.device).cuda_stream)
         else:  # gather: the reference algorithm, one collective + one fold launch per bucket

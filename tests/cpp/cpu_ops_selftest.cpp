@@ -71,7 +71,35 @@ static void check_static_casts() {
   if (bad) failures += (int)bad;
 }
 
+// the hardware pack path's algorithm: IEEE RNE convert of pretruncate(x) == reference cast, below the overflow band
+template <int E, int M>
+static void check_pretruncate(float limit) {
+  const cpd::Format fr = cpd::make_format(E, M, cpd::ROUND_REF), fi = cpd::make_format(E, M, cpd::ROUND_IEEE);
+  long bad = 0, n = 0;
+  std::mt19937 rng(E * 1000 + M);
+  auto one = [&](float x) {
+    if (!(std::fabs(x) < limit)) return;                 // NaN / Inf / overflow band take the software path on the GPU too
+    ++n;
+    const float want = cpd::quantize_ref(x, fr);
+    const float got = cpd::quantize_ieee(cpd::pretruncate<E, M>(x), fi);
+    if (!same(got, want) && ++bad <= 5) std::fprintf(stderr, "FAIL pretruncate (%d,%d) x=%a: %a want %a\n", E, M, x, got, want);
+  };
+  const uint32_t lows[] = {0x0000u, 0x0001u, 0x7FFFu, 0x8000u, 0x8001u, 0xFFFFu, 0x1234u, 0xFFF0u};
+  for (uint32_t hi = 0; hi < 65536u; ++hi)
+    for (uint32_t lo : lows) one(from_bits((hi << 16) | lo));
+  const int lo_e = cpd::FormatT<E, M>::lo;
+  for (int i = 0; i < 4000000; ++i) {
+    int e = lo_e + 3 - int(rng() % 32u);
+    if (e < 0) e = 0;
+    one(from_bits((rng() & 0x807FFFFFu) | (uint32_t(e) << 23)));
+  }
+  if (bad) failures += (int)bad;
+  std::printf("pretruncate (%d,%d): %ld patterns below %g checked\n", E, M, n, limit);
+}
+
 int main() {
+  check_pretruncate<4, 3>(248.0f);
+  check_pretruncate<5, 2>(61440.0f);
   std::mt19937 rng(1234);
   check_static_casts<4, 3>(); check_static_casts<5, 2>(); check_static_casts<5, 10>(); check_static_casts<8, 7>();
   check_static_casts<8, 23>(); check_static_casts<3, 0>(); check_static_casts<2, 1>(); check_static_casts<8, 0>();
