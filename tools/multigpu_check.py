@@ -83,6 +83,28 @@ def time_calls(fn, iters, warm=3):
     return max_over_ranks(e0.elapsed_time(e1) / iters)
 
 
+def time_calls_restored(fn, restore, iters, warm=2):
+    """Per-call CUDA events around fn(); restore() runs between the calls, outside the timed region.  For large
+    messages (launch latency negligible): the SAME buffer is reduced every time, like a training step's gradient
+    arena (warm TLB), while the values stay those of the original gradients."""
+    for _ in range(warm):
+        restore()
+        fn()
+    dist.barrier()
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(iters):
+        restore()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    return max_over_ranks(total / iters)
+
+
 def same_bits(a, b):
     return bool(((a.view(torch.int32) == b.view(torch.int32)) | (a.isnan() & b.isnan())).all())
 
@@ -229,6 +251,11 @@ def section_sweep(rank, world, res, max_bytes):
             row[f"fused_{algo}_busbw_fp32_GBps"] = round(nbytes / (ms * 1e-3) * 2 * (world - 1) / world / 1e9, 2)
             row[f"fused_{algo}_wire_GBps"] = round((n * red.wire / 8) / (ms * 1e-3) * 2 * (world - 1) / world / 1e9, 2)
             row[f"fused_{algo}_finite_after"] = bool(torch.isfinite(pool).all())
+            if nbytes >= (1 << 26) and algo in ("twoshot", "nvls"):
+                # training-like access pattern: one arena, reduced in place every step, values restored off the clock
+                g = arena.grad_flat
+                ms = time_calls_restored(lambda: red.reduce(), lambda: g.copy_(orig), max(iters // 2, 4))
+                row[f"fused_{algo}_same_buffer_us"] = round(ms * 1e3, 2)
             del red
         for kname, kalgo in (("auto", "auto"),):
             redk = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, use_kahan=True, algo=kalgo), mode="fused")
@@ -244,6 +271,10 @@ def section_sweep(rank, world, res, max_bytes):
         refill()
         ms = time_calls(lambda: dist.all_reduce(next_buf()), iters)
         row["nccl_fp32_allreduce_us"] = round(ms * 1e3, 2)
+        if nbytes >= (1 << 26):
+            g = arena.grad_flat
+            ms2 = time_calls_restored(lambda: dist.all_reduce(g), lambda: g.copy_(orig), max(iters // 2, 4))
+            row["nccl_fp32_same_buffer_us"] = round(ms2 * 1e3, 2)
         row["nccl_fp32_busbw_GBps"] = round(nbytes / (ms * 1e-3) * 2 * (world - 1) / world / 1e9, 2)
         if nbytes <= (1 << 28):
             gb = torch.empty(world, orig.numel(), device=dev)
