@@ -50,6 +50,25 @@ def test_quantize_variants():
     assert ab.view(torch.float32).item() == x.abs().max().item()
 
 
+def test_quantize_more_than_2_31_elements():
+    """64-bit indexing (the reference truncates the size to int, quant.cu:17): 2^31 + 4099 elements in place."""
+    n = (1 << 31) + 4099
+    free, _ = torch.cuda.mem_get_info()
+    if free < n * 4 + (1 << 30):
+        pytest.skip("not enough free device memory")
+    x = torch.empty(n, device="cuda")
+    x.fill_(1.2345)
+    x[-4099:] = torch.linspace(-3.0, 3.0, 4099, device="cuda")
+    tail = x[-4099:].clone().cpu()
+    float_quantize(x, 4, 3, inplace=True)
+    assert _same(x[-4099:], float_quantize(tail, 4, 3))
+    assert _same(x[:1024], float_quantize(torch.full((1024,), 1.2345), 4, 3))
+    mid = (1 << 31) - 512
+    assert _same(x[mid:mid + 1024], float_quantize(torch.full((1024,), 1.2345), 4, 3))
+    del x
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("M,N,K", [(64, 64, 64), (1, 1, 1), (17, 65, 33), (130, 70, 257), (10, 512, 48)])
 @pytest.mark.parametrize("e,m,kahan", [(4, 3, True), (5, 2, True), (5, 10, False), (8, 23, True)])
 def test_gemm_exact_matches_cpu(M, N, K, e, m, kahan):
