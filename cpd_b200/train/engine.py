@@ -17,14 +17,13 @@ the device, so graph replay needs no host-side bookkeeping.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Sequence
+import os
+from typing import Optional, Sequence
 
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
-
-import os
 
 from ..config import PrecisionConfig
 from ..optim import FusedSGD
@@ -43,7 +42,7 @@ class TrainEngine:
                  nesterov: bool = False, wd_mult: Optional[Sequence[float]] = None, loss_reduction: str = "mean",
                  loss_scale: float = 1.0, channels_last: bool = True, cuda_graph: bool = True,
                  fold_single: bool = False, device: Optional[torch.device] = None, master_weights: bool = True,
-                 lars_eps: float = 0.0, warmup_steps: int = 3):
+                 lars_eps: float = 0.0, warmup_steps: int = 3, amp_dtype: Optional[torch.dtype] = None):
         self.cfg = cfg
         self.distributed = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size() if self.distributed else 1
@@ -55,6 +54,9 @@ class TrainEngine:
         self.E = int(cfg.emulate_node)
         self.batch_size = int(batch_size)
         self.loss_reduction, self.loss_scale = loss_reduction, float(loss_scale)
+        # reduced-precision COMPUTE (the reference's dawn.py --half): autocast around forward + loss; parameters,
+        # gradients, masters and the whole gradient path stay fp32, so the low-bit all-reduce semantics are untouched
+        self.amp_dtype = amp_dtype
 
         model = model.to(device)
         self.channels_last = bool(channels_last and self.is_cuda)
@@ -97,8 +99,9 @@ class TrainEngine:
             xin = self.x[k]
             if self.channels_last:
                 xin = xin.contiguous(memory_format=torch.channels_last)
-            out = self.model(xin)
-            loss = self._loss(out, self.y[k]) / denom
+            with torch.autocast(device_type=self.device.type, dtype=self.amp_dtype or torch.bfloat16, enabled=self.amp_dtype is not None):
+                out = self.model(xin)
+            loss = self._loss(out.float(), self.y[k]) / denom
             if overlap:
                 self.reducer.arm()
             (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
@@ -170,7 +173,9 @@ class TrainEngine:
         x = images.to(self.device, non_blocking=True)
         if self.channels_last:
             x = x.contiguous(memory_format=torch.channels_last)
-        out = self.model(x)
+        with torch.autocast(device_type=self.device.type, dtype=self.amp_dtype or torch.bfloat16, enabled=self.amp_dtype is not None):
+            out = self.model(x)
+        out = out.float()
         y = labels.to(self.device, non_blocking=True)
         loss = F.cross_entropy(out, y)
         self.model.train(was)

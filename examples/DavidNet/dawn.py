@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--lr_scale", default=1.0, type=float)
     ap.add_argument("--seed", default=0, type=int)
     ap.add_argument("--loss_scale", default=1, type=int)
+    ap.add_argument("--half", default=0, type=int, help="1: fp16 forward/backward (autocast), as the reference's --half; gradients stay fp32")
+    ap.add_argument("--bf16", action="store_true", help="bf16 forward/backward (autocast)")
     ap.add_argument("--data", default="")
     ap.add_argument("--dataset_len", default=50000, type=int)
     add_precision_args(ap, grad_exp=8, grad_man=23)
@@ -44,7 +46,8 @@ def main():
     cfg = PrecisionConfig.from_args(args)
     B = args.batch_size
     engine = TrainEngine(create_model("davidnet"), cfg, batch_size=B, lr=0.0, momentum=args.momentum, weight_decay=5e-4 * B,
-                         nesterov=not args.use_lars, use_lars=args.use_lars, loss_reduction="sum", loss_scale=args.loss_scale)
+                         nesterov=not args.use_lars, use_lars=args.use_lars, loss_reduction="sum", loss_scale=args.loss_scale,
+                         amp_dtype=torch.bfloat16 if args.bf16 else (torch.float16 if args.half else None))
     if args.data:
         import torchvision
         raw = torchvision.datasets.CIFAR10(args.data, train=True)

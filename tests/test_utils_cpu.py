@@ -226,3 +226,19 @@ def test_committed_profiles_hold_the_perf_floors():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_perf_floors.py")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_engine_autocast_compute_keeps_fp32_gradient_path():
+    """dawn.py --half / --bf16: forward/backward under autocast, parameters + gradients + all-reduce path stay fp32."""
+    from cpd_b200.train import TrainEngine
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(48, 32), torch.nn.ReLU(), torch.nn.Linear(32, 10))
+    eng = TrainEngine(m, PrecisionConfig(grad_exp=5, grad_man=2, use_aps=True), batch_size=8, input_shape=(3, 4, 4), lr=0.05,
+                      use_lars=False, cuda_graph=False, amp_dtype=torch.bfloat16)
+    x, y = torch.randn(8, 3, 4, 4), torch.randint(0, 10, (8,))
+    first = eng.train_step(x, y)
+    for _ in range(20):
+        last = eng.train_step(x, y)
+    assert last < first and eng.arena.grad_flat.dtype == torch.float32 and all(p.dtype == torch.float32 for p in m.parameters())
+    out, loss = eng.evaluate(x, y)
+    assert out.dtype == torch.float32 and torch.isfinite(loss)
