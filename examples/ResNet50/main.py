@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--momentum", type=float, default=0.9)
     ap.add_argument("--wd", type=float, default=1e-4)
     ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--no-cuda", action="store_true", help="run on the CPU backend (C++ CPU ops, Gloo)")
     ap.add_argument("--data", default="", help="ImageFolder root with train/ and val/; synthetic if empty")
     ap.add_argument("--dataset-len", type=int, default=4096)
     ap.add_argument("--max-iter", type=int, default=0)
@@ -47,7 +48,8 @@ def main():
     cfg = PrecisionConfig.from_args(args)
     model = create_model("resnet50")
     engine = TrainEngine(model, cfg, batch_size=args.batch_size, input_shape=(3, 224, 224), lr=args.base_lr, momentum=args.momentum,
-                         weight_decay=args.wd, nesterov=True, wd_mult=bn_bias_no_decay(model.named_parameters()), fold_single=True)
+                         weight_decay=args.wd, nesterov=True, wd_mult=bn_bias_no_decay(model.named_parameters()), fold_single=True,
+                         device=torch.device("cpu") if args.no_cuda else None)
     if args.data:
         import torchvision.datasets as D
         import torchvision.transforms as T
