@@ -161,6 +161,34 @@ def test_engine_graph_matches_eager_and_learns():
     assert np.allclose(runs[0], runs[1], rtol=2e-2), runs
 
 
+def test_overlapped_bucketed_reduce_equals_sequential():
+    """buckets reduced on the comm stream as soon as their gradients are ready (hooks, eager and captured
+    in a CUDA graph) give the same weights as reducing the same buckets after backward."""
+    from cpd_b200.train import TrainEngine
+
+    def run(overlap, graph):
+        torch.manual_seed(0)
+        layers = []
+        for _ in range(6):
+            layers += [torch.nn.Linear(256, 256), torch.nn.ReLU()]
+        m = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 8 * 8, 256), torch.nn.ReLU(), *layers, torch.nn.Linear(256, 10))
+        eng = TrainEngine(m, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, bucket_mb=0.3, overlap=overlap), batch_size=64,
+                          input_shape=(3, 8, 8), lr=0.05, use_lars=False, cuda_graph=graph, warmup_steps=1, channels_last=False)
+        assert len(eng.reducer.buckets) >= 4
+        g = torch.Generator().manual_seed(1)
+        x, y = torch.randn(64, 3, 8, 8, generator=g).pin_memory(), torch.randint(0, 10, (64,), generator=g).pin_memory()
+        losses = [eng.train_step(x, y) for _ in range(5)]
+        torch.cuda.synchronize()
+        return eng.arena.model_flat.clone(), losses
+
+    w_seq, l_seq = run(False, False)
+    for overlap, graph in ((True, False), (True, True), (False, True)):
+        w, l = run(overlap, graph)
+        assert torch.allclose(w, w_seq, rtol=1e-5, atol=1e-7), (overlap, graph, float((w - w_seq).abs().max()))
+        assert np.allclose(l, l_seq, rtol=1e-5), (overlap, graph, l, l_seq)
+    assert l_seq[-1] < l_seq[0]
+
+
 def test_engine_emulate_node_equals_cpu_semantics():
     """emulate_node=4 on the GPU == the C++ CPU op on the same micro-gradients (bitwise)."""
     from cpd_b200.parallel import ModelArena, EmulateNode
