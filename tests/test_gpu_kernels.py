@@ -354,12 +354,12 @@ def test_fused_allreduce_fake_world_matches_cpu_fold(world):
     """The cross-GPU kernel on ONE GPU: it is told world_size = W while every peer pointer aliases local memory
     (tools/fake_world.py), so the raw and packed one-shot variants run their full W-rank instruction stream —
     amax, exponent mailboxes, scale + cast + pack, W-rank decode + fold (plain and Kahan), unscale — and the result
-    must equal the pure-software CPU fold of W copies bit for bit, incl. tensors with NaN / Inf / zeros."""
+    must equal the pure-software CPU fold of W copies bit for bit, incl. tensors with NaN / Inf / zeros / fp32 denormals."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29700 + world + os.getpid() % 200))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fake_world.py"), "--check-only", "--no-denormals", "--world", str(world)],
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fake_world.py"), "--check-only", "--world", str(world)],
                        capture_output=True, text=True, timeout=280, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "mismatching cases: none" in r.stdout, r.stdout[-3000:]

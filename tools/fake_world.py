@@ -48,6 +48,11 @@ def fake(red):
     from cuda.bindings import runtime as rt
     mb_init = torch.full(((s.off_flags - s.off_mailbox) // 4,), float("-inf"), dtype=torch.float32, device=dev)
     flag_init = torch.full((FLAG_WORDS,), 1 << 30, dtype=torch.int32, device=dev)
+    # ... but NOT this rank's own slots: CTA 0's release of each phase is what orders its exponent push / wire data
+    # before the other CTAs' reads.  (A first version pre-set them too; the other CTAs then raced past the exponent
+    # exchange of the first launch and could read a not-yet-written mailbox entry - seen as an all-zero result for the
+    # one tensor whose exponent takes longest to compute, the fp32-denormal one.)
+    flag_init.view(3, FLAG_WORDS // 3)[:, 0] = 0
     torch.cuda.synchronize()
     for off, d in ((s.off_mailbox, mb_init), (s.off_flags, flag_init)):
         err, = rt.cudaMemcpy(base + off, d.data_ptr(), d.numel() * 4, rt.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
