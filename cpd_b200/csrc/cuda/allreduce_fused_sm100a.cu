@@ -51,6 +51,7 @@ struct ArParams {
   int n_chunks, T;
   int use_aps, algo, prequant, ident;
   int pack_hw;           // opt-in (algo bit 8): hardware scale+cast+pack of phase B for the fp8-shaped formats
+  int poll_cta0;         // opt-in (algo bit 9): only CTA 0 polls the peers' flags, the others poll a local go-flag
   unsigned* ws;          // [0],[1] grid barrier; [2] epoch; [3] status; [4..4+2*max_tensors) amax[2][max_tensors]
   int* shifts_out;
   unsigned long long timeout;
@@ -158,15 +159,30 @@ __device__ __forceinline__ void signal_peers(const ArParams& p, int phase, unsig
   }
 }
 // every CTA waits until all peers have published `epoch` for `phase` (bounded spin).
+// Default: W threads of EVERY CTA poll the peers' flags.  Opt-in (poll_cta0, algo bit 9): only CTA 0 polls the line
+// the peers' release-stores land in and republishes a local go-flag (release/acquire at gpu scope) that the other
+// CTAs poll - 296 x W pollers no longer compete with the incoming NVLink writes for that one L2 line.
 __device__ __forceinline__ void wait_peers(const ArParams& p, int phase, unsigned epoch) {
-  if (threadIdx.x < p.world) {
-    const unsigned* f = p.flags[p.rank] + phase * kFlagStride + threadIdx.x;
-    const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(f) - epoch) < 0) {
-      if ((unsigned long long)(clock64() - t0) > p.timeout) {
-        atomicExch(&p.ws[3], 0x80000000u | (unsigned(phase) << 8) | threadIdx.x);   // who is missing
-        break;
+  unsigned* go = p.ws + 4 + 2 * p.max_tensors + 26 + phase;
+  if (!p.poll_cta0 || blockIdx.x == 0) {
+    if (threadIdx.x < p.world) {
+      const unsigned* f = p.flags[p.rank] + phase * kFlagStride + threadIdx.x;
+      const long long t0 = clock64();
+      while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+        if ((unsigned long long)(clock64() - t0) > p.timeout) {
+          atomicExch(&p.ws[3], 0x80000000u | (unsigned(phase) << 8) | threadIdx.x);   // who is missing
+          break;
+        }
       }
+    }
+    if (p.poll_cta0) {
+      __syncthreads();
+      if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(go), "r"(epoch) : "memory");
+    }
+  } else if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_gpu(go) - epoch) < 0) {
+      if ((unsigned long long)(clock64() - t0) > 2 * p.timeout) break;      // CTA 0 reports the missing peer
     }
   }
   __syncthreads();
@@ -543,6 +559,7 @@ void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunk
   p.grad = grad; p.chunks = chunks; p.n_chunks = n_chunks; p.T = T;
   p.use_aps = use_aps; p.algo = algo & 0xFF; p.prequant = prequant;
   p.pack_hw = (algo >> 8) & 1;
+  p.poll_cta0 = (algo >> 9) & 1;
   p.ident = (e == 8 && m == 23 && !kahan) ? 1 : 0;
   p.ws = local_ws; p.shifts_out = shifts_out; p.timeout = timeout_cycles;
   if (p.algo == ALGO_NVLS && !cb.mc_gather) p.algo = ALGO_TWOSHOT;
