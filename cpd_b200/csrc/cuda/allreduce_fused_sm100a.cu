@@ -52,6 +52,7 @@ struct ArParams {
   int use_aps, algo, prequant, ident;
   int pack_hw;           // opt-in (algo bit 8): hardware scale+cast+pack of phase B for the fp8-shaped formats
   int poll_cta0;         // opt-in (algo bit 9): only CTA 0 polls the peers' flags, the others poll a local go-flag
+  int weak_loads;        // opt-in (algo bit 10): plain instead of system-scope strong loads for the peers' wire data
   unsigned* ws;          // [0],[1] grid barrier; [2] epoch; [3] status; [4..4+2*max_tensors) amax[2][max_tensors]
   int* shifts_out;
   unsigned long long timeout;
@@ -69,6 +70,16 @@ __device__ __forceinline__ Granule<WIRE> granule_load_sys(const unsigned char* b
   const unsigned char* p = base + elem * (WIRE / 8);
 #pragma unroll
   for (int i = 0; i < WIRE / 8; ++i) g.v[i] = ld_sys_u4(p + 16 * i);
+  return g;
+}
+// same through plain (weak) loads: legal after the acquire of the data flag, which orders them; the L1 cannot hold a
+// stale copy because every wire buffer is read once per launch and the L1 is invalidated at launch boundaries
+template <int WIRE>
+__device__ __forceinline__ Granule<WIRE> granule_load_weak(const unsigned char* base, long long elem) {
+  Granule<WIRE> g;
+  const uint4* p = reinterpret_cast<const uint4*>(base + elem * (WIRE / 8));
+#pragma unroll
+  for (int i = 0; i < WIRE / 8; ++i) g.v[i] = p[i];
   return g;
 }
 template <int WIRE>
@@ -289,7 +300,8 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
         uint4 in[kArMaxW];
 #pragma unroll
         for (int r = 0; r < kArMaxW; ++r)
-          if (r < W) in[r] = ld_sys_u4(p.data[r] + par * p.cap_bytes + e0 * 4);
+          if (r < W) in[r] = p.weak_loads ? *reinterpret_cast<const uint4*>(p.data[r] + par * p.cap_bytes + e0 * 4)
+                                          : ld_sys_u4(p.data[r] + par * p.cap_bytes + e0 * 4);
         float s4[4] = {0.f, 0.f, 0.f, 0.f}, c4[4] = {0.f, 0.f, 0.f, 0.f};
         // rolled on purpose (the peers' vectors sit in a small local array): unrolling over 8 ranks only multiplies the code
 #pragma unroll 1
@@ -440,7 +452,8 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
       if (WIRE <= 16) {
 #pragma unroll
         for (int r = 0; r < kPre; ++r)
-          if (r < W) in[r] = granule_load_sys<WIRE>(p.data[r] + par * p.cap_bytes, e0);
+          if (r < W) in[r] = p.weak_loads ? granule_load_weak<WIRE>(p.data[r] + par * p.cap_bytes, e0)
+                                          : granule_load_sys<WIRE>(p.data[r] + par * p.cap_bytes, e0);
       }
       if (first && WIRE <= 16) {
         unsigned acc = 0u;
@@ -560,6 +573,7 @@ void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunk
   p.use_aps = use_aps; p.algo = algo & 0xFF; p.prequant = prequant;
   p.pack_hw = (algo >> 8) & 1;
   p.poll_cta0 = (algo >> 9) & 1;
+  p.weak_loads = (algo >> 10) & 1;
   p.ident = (e == 8 && m == 23 && !kahan) ? 1 : 0;
   p.ws = local_ws; p.shifts_out = shifts_out; p.timeout = timeout_cycles;
   if (p.algo == ALGO_NVLS && !cb.mc_gather) p.algo = ALGO_TWOSHOT;
