@@ -66,7 +66,7 @@ def _case_sum_gradients(rank, world):
     return out
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_sum_gradients_gloo_matches_oracle(world):
     from oracle import aps_fold_oracle
     res = _run("_case_sum_gradients", world)
