@@ -55,7 +55,8 @@ void gemm_exact_cuda(const float* A, int64_t sa0, int64_t sa1, const float* B, i
                      float* C, int64_t ldc, int M, int N, int K, int e, int m, int rounding, bool kahan,
                      cudaStream_t st);
 
-// Multi-source APS fold (local sources: emulate_node slots, or W==1): one launch.
+// Multi-source APS fold (local sources: emulate_node slots, or W==1): one launch, up to kMaxLocalSources arenas.
+constexpr int kMaxLocalSources = 64;
 //   srcs: device array of W pointers to flat fp32 arenas sharing the chunk table
 //   workspace: 4 + 2*T_cap unsigned (grid barrier, launch counter, amax[2][T_cap]), zeroed once
 void aps_fold_local_cuda(const float* const* srcs, int W, float* out, const Chunk* chunks,

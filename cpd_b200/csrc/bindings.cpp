@@ -112,7 +112,7 @@ PYBIND11_MODULE(_C, m) {
   m.def("aps_fold_cuda", [](std::vector<uptr> srcs, uptr out, uptr chunks, int n_chunks, int T, int T_cap, int e, int mb, bool use_aps,
                             bool kahan, double world_mult, uptr workspace, uptr shifts_out, int max_ctas, uptr stream) {
     check_fmt(e, mb);
-    if (srcs.empty() || srcs.size() > 16) throw std::invalid_argument("aps_fold: 1..16 sources");
+    if (srcs.empty() || srcs.size() > (size_t)cpd::kMaxLocalSources) throw std::invalid_argument("aps_fold: 1..64 sources");
     std::vector<const float*> ptrs;
     for (auto s : srcs) ptrs.push_back(P<const float>(s));
     cpd::aps_fold_local_cuda(ptrs.data(), (int)ptrs.size(), P<float>(out), P<const cpd::Chunk>(chunks), n_chunks, T, T_cap, e, mb, use_aps,

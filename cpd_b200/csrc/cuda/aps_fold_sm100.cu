@@ -20,7 +20,7 @@
 namespace cpd {
 
 constexpr int kFoldThreads = 256;
-constexpr int kMaxLocalSrc = 16;
+constexpr int kMaxLocalSrc = kMaxLocalSources;   // api.h: 64 (the reference's README runs --emulate-node 32)
 
 struct SrcPtrs { const float* p[kMaxLocalSrc]; };
 

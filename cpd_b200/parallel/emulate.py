@@ -30,8 +30,8 @@ class EmulateNode:
         self.ws = None
         self.shifts = None
         if self.active:
-            if self.E > 16:
-                raise ValueError("emulate_node > 16 is not supported by the fold kernel")
+            if self.E > 64:
+                raise ValueError("emulate_node > 64 is not supported by the fold kernel")
             self.slots = [arena.layout.new(arena.device) for _ in range(self.E)]
             self.table = arena.table()
             self.shifts = torch.zeros(self.table.T, dtype=torch.int32, device=arena.device)

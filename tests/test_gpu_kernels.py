@@ -93,7 +93,7 @@ def _arenas(W, numels, seed, device):
     return layout, out
 
 
-@pytest.mark.parametrize("W", [1, 2, 8])
+@pytest.mark.parametrize("W", [1, 2, 8, 32])
 @pytest.mark.parametrize("e,m", [(4, 3), (5, 2), (5, 10), (6, 9)])
 @pytest.mark.parametrize("aps,kahan", [(True, False), (True, True), (False, False), (False, True)])
 def test_aps_fold_matches_cpu(W, e, m, aps, kahan):

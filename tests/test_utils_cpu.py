@@ -130,24 +130,25 @@ def test_loggers(tmp_path, capsys):
     assert "epoch" in capsys.readouterr().out
 
 
-def test_emulate_node_equals_multi_rank_fold():
+@pytest.mark.parametrize("E", [4, 32])          # 32: the reference README's "8 GPUs emulate 256 nodes" setting
+def test_emulate_node_equals_multi_rank_fold(E):
     """emulate_node=E on one process == the W=E fold of the same micro-gradients (bitwise)."""
     from cpd_b200.parallel import ModelArena, EmulateNode
     from cpd_b200.ops import native
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(12, 9), torch.nn.Tanh(), torch.nn.Linear(9, 3))
     arena = ModelArena(list(net.parameters()))
-    cfg = PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, emulate_node=4)
+    cfg = PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, emulate_node=E)
     em = EmulateNode(arena, cfg)
-    xs = [torch.randn(5, 12) for _ in range(4)]
+    xs = [torch.randn(5, 12) for _ in range(E)]
     micro = []
-    for k in range(4):
+    for k in range(E):
         em.begin_micro(k)
-        (net(xs[k]).square().mean() / 4).backward()
+        (net(xs[k]).square().mean() / E).backward()
         micro.append(em.slots[k].clone())
     em.fold()
     want = torch.empty(arena.layout.total)
-    native.aps_fold(micro, want, arena.layout.table("cpu").seg_off, 4, 3, True, False, 4.0)
+    native.aps_fold(micro, want, arena.layout.table("cpu").seg_off, 4, 3, True, False, float(E))
     assert torch.equal(arena.grad_flat, want)
     assert net[0].weight.grad.data_ptr() == arena.grad_views[0].data_ptr()
 
