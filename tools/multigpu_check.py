@@ -115,6 +115,9 @@ def all_ranks_equal(t, world):
     return all(same_bits(buf[0], b) for b in buf[1:])
 
 
+SPECIALS = False      # --specials: add a layout whose tensors carry NaN / Inf / zeros / fp32 denormals on different ranks
+
+
 def section_correct(rank, world, res):
     layouts = {"tiny": [1, 10, 64, 5], "mixed": [10, 64, 1, 4097, 300, 70000, 5, 128, 36864], "r18": None}
     from cpd_b200.models import create_model
@@ -126,11 +129,25 @@ def section_correct(rank, world, res):
              dict(grad_exp=6, grad_man=9, use_aps=True, use_kahan=True)]
     out = []
     dev = torch.device("cuda", torch.cuda.current_device())
+    if SPECIALS:
+        layouts["specials"] = [4112, 1000, 64, 16, 7777, 300, 48]
     for lname, numels in layouts.items():
         arena = FakeArena(numels, dev)
         for ci, kw in enumerate(cases):
             oracle = GradReducer(arena, PrecisionConfig(**kw), mode="gather")
             fill(arena, rank, seed=ci * 7 + len(numels))
+            if lname == "specials":
+                # exceptional values, placed on different ranks: NaN, +Inf, an all-zero tensor, -Inf, fp32 denormals
+                off, g = arena.layout.offsets, arena.grad_flat
+                if rank == 0:
+                    g[off[1] + 5] = float("nan")
+                if rank == world - 1:
+                    g[off[2] + 3] = float("inf")
+                g[off[3]:off[3] + 16] = 0.0
+                if rank == 1 % world:
+                    g[off[4] + 11] = -float("inf")
+                gen = torch.Generator().manual_seed(1000 * rank + ci)
+                g[off[5]:off[5] + 300] = (torch.randn(300, generator=gen) * 1e-41).to(dev)
             mine = arena.grad_flat.clone()
             if kw.get("grad_exp") == 8 and kw.get("grad_man") == 23 and not kw.get("use_kahan") and not kw.get("use_aps"):
                 # plain fp32: the gather-mode path is NCCL's all_reduce (its own summation order); the fused kernel sums in
@@ -301,7 +318,10 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--stress-iters", type=int, default=2000)
     ap.add_argument("--max-bytes", type=int, default=1 << 30)
+    ap.add_argument("--specials", action="store_true", help="correct section: also a layout with NaN / Inf / zero / denormal tensors")
     args = ap.parse_args()
+    global SPECIALS
+    SPECIALS = bool(args.specials)
     rank, world = dist_init()
     res = {"world": world, "torch": torch.__version__}
     secs = args.sections.split(",")

@@ -10,7 +10,7 @@ port=29950
 for v in default PACK_HW POLL_CTA0 WEAK_LOADS; do
   port=$((port + 1))
   echo "== variant $v: check + sweep"
-  env $( [ $v = default ] && echo X=1 || echo CPD_B200_$v=1 ) timeout 420 $TR --master-port $port tools/multigpu_check.py --sections correct,sweep \
+  env $( [ $v = default ] && echo X=1 || echo CPD_B200_$v=1 ) timeout 420 $TR --master-port $port tools/multigpu_check.py --specials --sections correct,sweep \
     --max-bytes ${MAXB:-268435456} --out $OUT/check_sweep_$v.json > $OUT/check_sweep_$v.log 2>&1; echo "rc=$?"
   grep -E "^\[correct|FAIL|Error" $OUT/check_sweep_$v.log | head -4 | cut -c1-300
 done
