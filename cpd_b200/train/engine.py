@@ -81,6 +81,8 @@ class TrainEngine:
         self._warmup_left = int(warmup_steps) if self._use_graph else 0
         self._done_evt = torch.cuda.Event() if self.is_cuda else None
         self.kernel_launches_per_step = None
+        self._x_stage = self._y_stage = self._copy_stream = self._staged_evt = self._consumed_evt = None
+        self._stage_busy = self._consumed_recorded = False
 
     # ------------------------------------------------------------------ step body --
     def _loss(self, logits, target):
@@ -133,6 +135,65 @@ class TrainEngine:
         """Host -> device copy of one step's inputs ([E*B, ...] or [E, B, ...]); pinned sources are async."""
         self.x.view(-1, *self.x.shape[2:]).copy_(images.view(-1, *self.x.shape[2:]), non_blocking=True)
         self.y.view(-1).copy_(labels.view(-1), non_blocking=True)
+
+    # -- input pipelining: the H2D copy of step i+1 overlaps the compute of step i --------------------------------
+    def prefetch(self, images: torch.Tensor, labels: torch.Tensor) -> None:
+        """Start the host -> device copy of the NEXT step's inputs into a staging buffer on a copy stream (pinned
+        sources make it asynchronous); `train_step_pipelined` / `begin_step` consume it."""
+        if self._x_stage is None:
+            self._x_stage, self._y_stage = torch.empty_like(self.x), torch.empty_like(self.y)
+            if self.is_cuda:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+                self._staged_evt, self._consumed_evt = torch.cuda.Event(), torch.cuda.Event()
+        if self.is_cuda:
+            if self._consumed_recorded:
+                self._copy_stream.wait_event(self._consumed_evt)          # the previous staged batch has been taken over
+            with torch.cuda.stream(self._copy_stream):
+                self._x_stage.view(-1, *self.x.shape[2:]).copy_(images.view(-1, *self.x.shape[2:]), non_blocking=True)
+                self._y_stage.view(-1).copy_(labels.view(-1), non_blocking=True)
+                self._staged_evt.record(self._copy_stream)
+        else:
+            self._x_stage.view(-1, *self.x.shape[2:]).copy_(images.view(-1, *self.x.shape[2:]))
+            self._y_stage.view(-1).copy_(labels.view(-1))
+        self._stage_busy = True
+
+    def begin_step(self, lr: Optional[float] = None) -> None:
+        """Take over the prefetched batch (device-to-device, a few us) and launch the step; returns immediately."""
+        if not self._stage_busy:
+            raise RuntimeError("begin_step() without a prefetched batch")
+        if lr is not None:
+            self.set_lr(lr)
+        if self.is_cuda:
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(self._staged_evt)
+            self.x.copy_(self._x_stage, non_blocking=True)
+            self.y.copy_(self._y_stage, non_blocking=True)
+            self._consumed_evt.record(cur)
+            self._consumed_recorded = True
+        else:
+            self.x.copy_(self._x_stage)
+            self.y.copy_(self._y_stage)
+        self.run_step()
+
+    def end_step(self) -> float:
+        """Device -> host read of the step's (local, already /W) loss."""
+        if self.is_cuda:
+            self.loss_host.copy_(self.loss_dev, non_blocking=True)
+            self._done_evt.record()
+            self._done_evt.synchronize()
+        else:
+            self.loss_host.copy_(self.loss_dev)
+        return float(self.loss_host[0])
+
+    def train_step_pipelined(self, next_images: Optional[torch.Tensor], next_labels: Optional[torch.Tensor],
+                             lr: Optional[float] = None) -> float:
+        """One step on the batch given to the previous `prefetch` / `train_step_pipelined` call while the next batch's
+        H2D copy runs on the copy stream.  Prime with `prefetch(first batch)`; pass None, None on the last step."""
+        self.begin_step(lr)
+        self._stage_busy = False
+        if next_images is not None:
+            self.prefetch(next_images, next_labels)
+        return self.end_step()
 
     def run_step(self) -> None:
         """One optimizer step on the inputs already in the static buffers (no host sync)."""

@@ -243,3 +243,23 @@ def test_engine_autocast_compute_keeps_fp32_gradient_path():
     assert last < first and eng.arena.grad_flat.dtype == torch.float32 and all(p.dtype == torch.float32 for p in m.parameters())
     out, loss = eng.evaluate(x, y)
     assert out.dtype == torch.float32 and torch.isfinite(loss)
+
+
+def test_pipelined_input_prefetch_equals_plain_steps():
+    """prefetch / train_step_pipelined (H2D of step i+1 behind the compute of step i) == the same batches through train_step."""
+    from cpd_b200.train import TrainEngine
+
+    def make():
+        torch.manual_seed(0)
+        m = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(48, 16), torch.nn.ReLU(), torch.nn.Linear(16, 10))
+        return TrainEngine(m, PrecisionConfig(grad_exp=5, grad_man=2, use_aps=True), batch_size=4, input_shape=(3, 4, 4), lr=0.05,
+                           use_lars=False, cuda_graph=False)
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.randn(4, 3, 4, 4, generator=g), torch.randint(0, 10, (4,), generator=g)) for _ in range(5)]
+    a, b = make(), make()
+    plain = [a.train_step(x, y) for x, y in batches]
+    b.prefetch(*batches[0])
+    piped = [b.train_step_pipelined(*(batches[i + 1] if i + 1 < len(batches) else (None, None))) for i in range(len(batches))]
+    assert piped == plain and torch.equal(a.arena.model_flat, b.arena.model_flat)
+    with pytest.raises(RuntimeError):
+        b.begin_step()
