@@ -27,3 +27,4 @@ for v in ("default", "PACK_HW", "POLL_CTA0", "WEAK_LOADS"):
             print("    raw phases", r.get("fused_raw_phases_us"), "\n    oneshot phases", {k: x for k, x in (r.get("fused_oneshot_phases_us") or {}).items() if k != "C_first_granule"})
 PY
 echo "== bench ours N=$N"; timeout 300 $TR --master-port 29970 bench.py --gpus $N --steps 40 --warmup 5 > $OUT/bench_ours.json 2> $OUT/bench_ours.err; echo "rc=$?"; cut -c1-400 $OUT/bench_ours.json
+echo "== bench ours N=$N, pipelined e2e"; timeout 300 $TR --master-port 29971 bench.py --gpus $N --steps 40 --warmup 5 --pipelined > $OUT/bench_ours_pipelined.json 2>> $OUT/bench_ours.err; echo "rc=$?"; cut -c1-400 $OUT/bench_ours_pipelined.json
