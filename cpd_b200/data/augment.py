@@ -22,6 +22,7 @@ def transpose(x, source="NHWC", target="NCHW"):
 
 
 class Crop:
+    """Random h x w crop with pre-drawn per-sample offsets (utils.py:89-101)."""
     def __init__(self, h, w):
         self.h, self.w = h, w
 
@@ -37,6 +38,7 @@ class Crop:
 
 
 class FlipLR:
+    """Random left-right flip with a pre-drawn per-sample choice (utils.py:104-112)."""
     def __call__(self, x, choice):
         return x[:, :, ::-1].copy() if choice else x
 
@@ -45,6 +47,7 @@ class FlipLR:
 
 
 class Cutout:
+    """Zeroes a random h x w patch, offsets pre-drawn per sample (utils.py:115-128)."""
     def __init__(self, h, w):
         self.h, self.w = h, w
 

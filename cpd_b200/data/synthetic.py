@@ -9,6 +9,8 @@ import torch
 
 
 class SyntheticImageDataset(torch.utils.data.Dataset):
+    """Random images / labels of a named shape (no dataset download in the sandbox); ``learnable=True`` makes the
+    label a function of the image so that accuracy can rise."""
     def __init__(self, n: int, shape=(3, 32, 32), num_classes: int = 10, seed: int = 0, learnable: bool = True):
         g = torch.Generator().manual_seed(seed)
         self.labels = torch.randint(0, num_classes, (n,), generator=g)

@@ -19,6 +19,7 @@ import torch.nn.functional as F
 
 
 class Scale(nn.Module):
+    """Multiplies by a constant (the reference's ``Mul``)."""
     def __init__(self, w: float):
         super().__init__()
         self.w = w
@@ -28,6 +29,7 @@ class Scale(nn.Module):
 
 
 class Add(nn.Module):
+    """Element-wise sum of two inputs (residual join)."""
     def forward(self, a, b):
         return a + b
 
@@ -96,16 +98,19 @@ def davidnet(channels=(64, 128, 256, 512), num_classes: int = 10, logit_scale: f
 
 # ---- dict-described networks (the reference's DavidNet is written this way) ------------------------------
 class Identity(nn.Module):
+    """Pass-through node."""
     def forward(self, x):
         return x
 
 
 class Concat(nn.Module):
+    """Channel-wise concatenation of its inputs."""
     def forward(self, *xs):
         return torch.cat(xs, 1)
 
 
 class Correct(nn.Module):
+    """Per-sample 0/1 correctness of the arg-max prediction."""
     def forward(self, logits, target):
         return logits.max(dim=1)[1] == target
 

@@ -33,6 +33,8 @@ class BasicBlock(nn.Module):
 
 
 class ResNetCifar(nn.Module):
+    """CIFAR ResNet of the reference (resnet18_cifar.py): 3x3 stem without max-pool, 4 stages of BasicBlocks,
+    ``avg_pool2d(4)``, linear head; ``forward(x, rank=None)`` keeps the reference's unused ``rank`` argument."""
     def __init__(self, blocks=(2, 2, 2, 2), widths=(64, 128, 256, 512), num_classes: int = 10):
         super().__init__()
         self.stem = nn.Sequential(_conv3x3(3, widths[0]), nn.BatchNorm2d(widths[0]), nn.ReLU(inplace=True))

@@ -53,6 +53,7 @@ class Basic(nn.Module):
 
 
 class ResNet(nn.Module):
+    """ImageNet ResNet-18/34/50/101 with torchvision's parameter layout (the reference uses torchvision.models.resnet50)."""
     def __init__(self, block, layers, num_classes=1000):
         super().__init__()
         self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)

@@ -18,6 +18,9 @@ from ..parallel.arena import ModelArena
 
 
 class FusedSGD:
+    """SGD / Nesterov / LARS on fp32 master weights in ONE multi-tensor launch per step (mix.py:292-314: master
+    copy, ``local_lr = 0.001 * |w| / (|g| + wd * |w|)``, momentum buffer, model <- master), learning rate read from
+    device memory so a captured CUDA graph can replay with a new value."""
     def __init__(self, arena: ModelArena, lr: float = 0.1, momentum: float = 0.9, weight_decay: float = 0.0,
                  use_lars: bool = False, lars_coeff: float = 0.001, lars_eps: float = 0.0, nesterov: bool = False,
                  wd_mult: Optional[Sequence[float]] = None, master_weights: bool = True):

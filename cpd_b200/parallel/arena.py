@@ -44,6 +44,8 @@ class ChunkTable:
 
 
 class ArenaLayout:
+    """Offsets of a list of tensors inside one flat fp32 buffer (every tensor starts on a 16-element boundary,
+    padding stays zero) and the chunk tables the multi-tensor kernels are scheduled by."""
     def __init__(self, numels: Sequence[int]):
         self.numels = [int(n) for n in numels]
         offs = [0]

@@ -19,6 +19,9 @@ from .arena import ModelArena
 
 
 class EmulateNode:
+    """One GPU plays ``cfg.emulate_node`` data-parallel nodes: autograd writes micro-batch k into slot arena k
+    (``begin_micro``), ``fold`` reduces the slots with the reference's local low-precision fold in one kernel
+    (mix.py:251-285, main.py:178-202).  Up to 64 slots."""
     def __init__(self, arena: ModelArena, cfg: PrecisionConfig, fold_single: bool = False):
         self.arena = arena
         self.cfg = cfg

@@ -18,6 +18,9 @@ from .api import sum_gradients
 
 
 class APSOptimizerHook:
+    """Optimizer hook in the style of the reference's mmcv fork (README.md:133-150): backward, low-precision
+    ``sum_gradients`` (APS / Kahan), optional gradient clipping, ``optimizer.step()``.  ``after_train_iter(runner)`` makes
+    it usable as an mmcv runner hook; ``step(model, optimizer, loss)`` works with any training loop."""
     def __init__(self, grad_exp: int = 5, grad_man: int = 2, use_APS: bool = True, use_kahan: bool = False,
                  grad_clip: Optional[dict] = None, precision: Optional[PrecisionConfig] = None):
         self.cfg = precision or PrecisionConfig(grad_exp=grad_exp, grad_man=grad_man, use_aps=use_APS, use_kahan=use_kahan)

@@ -55,6 +55,11 @@ RAW_MAX_ELEMS = 1024
 
 
 class GradReducer:
+    """Low-precision gradient all-reduce of a flat gradient arena (dist_util.py:22-89 semantics, bit for bit).
+
+    ``mode``: "fused" = one peer-memory kernel per bucket (raw / one-shot / two-shot / NVLS picked by size), "gather" =
+    the reference algorithm on NCCL/Gloo (all_gather + one fold launch; fallback and oracle), "local" = world size 1.
+    Buckets follow ``cfg.bucket_mb``; with ``cfg.overlap`` they launch from gradient hooks on a comm stream."""
     def __init__(self, arena: ModelArena, cfg: PrecisionConfig, group=None, mode: Optional[str] = None,
                  timeout_cycles: int = 20_000_000_000):
         self.arena = arena

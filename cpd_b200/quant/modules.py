@@ -58,6 +58,8 @@ class Quant_LinearFunction(Function):
 
 
 class Quant_Linear(nn.Module):
+    """``nn.Linear`` whose forward and backward GEMMs keep their accumulator at (exp, man) (quant_module.py:55-85):
+    ``mode="exact"`` = the reference's per-MAC casts, ``"tile"`` = tensor cores with a cast per K-slice, ``"auto"`` by size."""
     def __init__(self, in_features, out_features, bias=True, exp=8, man=23, mode="auto"):
         super().__init__()
         self.in_features, self.out_features = in_features, out_features

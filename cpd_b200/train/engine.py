@@ -37,6 +37,11 @@ _NVTX = os.environ.get("CPD_B200_NVTX", "0") == "1"      # NVTX ranges around fw
 
 
 class TrainEngine:
+    """One optimizer step per call, everything on the device (see the module docstring for the pipeline).
+
+    ``train_step(images, labels, lr=None) -> loss`` is the user call (H2D of the batch, captured step, D2H of the loss);
+    ``prefetch`` / ``train_step_pipelined`` hide the H2D copy behind the previous step; ``evaluate``, ``global_loss``,
+    ``comm_stats``, ``state_dict`` / ``load_state_dict`` complete the trainer-facing surface."""
     def __init__(self, model: nn.Module, cfg: PrecisionConfig, *, batch_size: int, input_shape: Sequence[int] = (3, 32, 32),
                  lr: float = 0.1, momentum: float = 0.9, weight_decay: float = 1e-4, use_lars: bool = False,
                  nesterov: bool = False, wd_mult: Optional[Sequence[float]] = None, loss_reduction: str = "mean",

@@ -9,6 +9,7 @@ from typing import Optional
 
 
 class TableLogger:
+    """Fixed-width column printer of the DavidNet recipe (utils.py:44-56): header on the first ``append``."""
     def __init__(self, rank: int = 0):
         self.rank, self.keys = rank, None
 
@@ -23,6 +24,7 @@ class TableLogger:
 
 
 class TSVLogger:
+    """Collects (epoch, hours, top1Accuracy) rows and prints them tab-separated (dawn.py:37-47, DAWNBench format)."""
     def __init__(self):
         self.log = ["epoch\thours\ttop1Accuracy"]
 
