@@ -118,6 +118,10 @@ def test_cpdtorch_facade_imports():
     from CPDtorch.quant import float_quantize, quantizer, Quantizer, quant_gemm, Quant_Linear, Quant_Conv  # noqa: F401
     from CPDtorch.utils.dist_util import dist_init, DistModule, sum_gradients, normal_sum_gradients, kahan_sum_gradients, broadcast_params  # noqa: F401
     assert float_quantize(torch.tensor([1.06]), 4, 3).item() == 1.0
+    # the reference's module paths work too (quant_function.py / quant_module.py)
+    from CPDtorch.quant.quant_function import float_quantize as fq2, quant_gemm as g2, quantizer as q2  # noqa: F401
+    from CPDtorch.quant.quant_module import Quantizer as Q2, Quant_Linear as L2, Quant_Conv as C2  # noqa: F401
+    assert fq2 is float_quantize and L2 is Quant_Linear
 
 
 def test_loggers(tmp_path, capsys):
