@@ -32,10 +32,16 @@ def available():
     return True, ""
 
 
-def setup_env(rank: int, world: int):
-    sys.path.insert(0, REF)
-    from prebuild_ref_ext import ref_env
-    ref_env()
+def setup_env(rank: int, world: int, lib: str = "reference"):
+    """lib="reference": CPDtorch resolves to the unmodified install in baseline/_ref (the benchmark arm).
+    lib="ours": the SAME recipes (and the reference's own example models) run on this repo's import-compatible
+    CPDtorch facade instead - the "user switches the library, keeps their trainer" scenario (tools/compat_run.py)."""
+    if lib == "ours":
+        sys.path.insert(0, os.path.dirname(HERE))                # repo root: CPDtorch/ facade + cpd_b200
+    else:
+        sys.path.insert(0, REF)
+        from prebuild_ref_ext import ref_env
+        ref_env()
     os.environ["SLURM_NODELIST"] = "hostname127-0-0-1"          # dist_util.py:109: node_list[8:].replace('-', '.')
     os.environ["SLURM_PROCID"] = str(rank)
     os.environ["SLURM_NTASKS"] = str(world)

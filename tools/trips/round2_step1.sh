@@ -24,3 +24,5 @@ for v in ("default", "PACK_HW", "POLL_CTA0", "WEAK_LOADS"):
               "| B", ph.get("B_pack+gridbar"), "flags", ph.get("exp_exchange"), ph.get("data_flags"), "C", ph.get("C_fold"))
 PY
 echo "== full GPU suite"; timeout 1500 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "rc=$?"; tail -3 $OUT/pytest_gpu.log
+echo "== library swap: the reference's ResNet-18 recipe on its own CPDtorch and on our facade"
+for lib in reference ours; do timeout 300 python tools/compat_run.py --lib $lib --model resnet18 --steps 6 2>$OUT/compat_$lib.err | tail -1 | tee $OUT/compat_$lib.json | cut -c1-300; done
