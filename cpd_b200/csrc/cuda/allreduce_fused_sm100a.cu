@@ -53,6 +53,7 @@ struct ArParams {
   int pack_hw;           // opt-in (algo bit 8): hardware scale+cast+pack of phase B for the fp8-shaped formats
   int poll_cta0;         // opt-in (algo bit 9): only CTA 0 polls the peers' flags, the others poll a local go-flag
   int weak_loads;        // opt-in (algo bit 10): plain instead of system-scope strong loads for the peers' wire data
+  int no_extra_fence;    // opt-in (algo bit 11): no __threadfence_system() in front of the release store of a flag
   unsigned* ws;          // [0],[1] grid barrier; [2] epoch; [3] status; [4..4+2*max_tensors) amax[2][max_tensors]
   int* shifts_out;
   unsigned long long timeout;
@@ -165,7 +166,9 @@ __device__ __forceinline__ void store16(float* p, const float (&x)[16]) {
 // CTA 0 publishes `epoch` for `phase` into every peer's signal pad.
 __device__ __forceinline__ void signal_peers(const ArParams& p, int phase, unsigned epoch) {
   if (blockIdx.x == 0 && threadIdx.x < p.world) {
-    __threadfence_system();
+    // st.release.sys already orders every earlier write (cumulatively) before the flag; the explicit fence in front of
+    // it is belt and braces and can be dropped with the opt-in bit (A/B for the flag-round latency)
+    if (!p.no_extra_fence) __threadfence_system();
     st_release_sys(p.flags[threadIdx.x] + phase * kFlagStride + p.rank, epoch);
   }
 }
@@ -574,6 +577,7 @@ void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunk
   p.pack_hw = (algo >> 8) & 1;
   p.poll_cta0 = (algo >> 9) & 1;
   p.weak_loads = (algo >> 10) & 1;
+  p.no_extra_fence = (algo >> 11) & 1;
   p.ident = (e == 8 && m == 23 && !kahan) ? 1 : 0;
   p.ws = local_ws; p.shifts_out = shifts_out; p.timeout = timeout_cycles;
   if (p.algo == ALGO_NVLS && !cb.mc_gather) p.algo = ALGO_TWOSHOT;

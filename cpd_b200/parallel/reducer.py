@@ -47,6 +47,8 @@ _PACK_HW = 0x100 if os.environ.get("CPD_B200_PACK_HW", "0") == "1" else 0
 _PACK_HW |= 0x200 if os.environ.get("CPD_B200_POLL_CTA0", "0") == "1" else 0
 # opt-in: plain loads for the peers' wire data in the fold (do 7 of them overlap better than strong sys-scope loads?)
 _PACK_HW |= 0x400 if os.environ.get("CPD_B200_WEAK_LOADS", "0") == "1" else 0
+# opt-in: drop the explicit system fence in front of the flags' release stores
+_PACK_HW |= 0x800 if os.environ.get("CPD_B200_NO_EXTRA_FENCE", "0") == "1" else 0
 _FAULT_DELAY_RANK = int(os.environ.get("CPD_B200_FAULT_DELAY_RANK", "-1"))
 _FAULT_DELAY_CYCLES = float(os.environ.get("CPD_B200_FAULT_DELAY_CYCLES", "2e8"))
 ONESHOT_MAX_BYTES = 512 * 1024

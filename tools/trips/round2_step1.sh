@@ -6,14 +6,14 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 OUT=gpurun_out/r2_step1; mkdir -p $OUT
 echo "== new GPU tests"; timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu \
   -k "fake_world or more_than_2_31 or overlapped or aps_fold or emulate" > $OUT/pytest_new.log 2>&1; echo "rc=$?"; tail -3 $OUT/pytest_new.log
-for v in default PACK_HW POLL_CTA0 WEAK_LOADS; do
+for v in default PACK_HW POLL_CTA0 WEAK_LOADS NO_EXTRA_FENCE; do
   echo "== fake world W=8, variant $v (check + timing)"
   env $( [ $v = default ] && echo X=1 || echo CPD_B200_$v=1 ) timeout 300 python tools/fake_world.py --max-bytes $((1<<26)) --out $OUT/fake8_$v.json > $OUT/fake8_$v.log 2>&1; echo "rc=$?"
   grep "fake-world check" $OUT/fake8_$v.log | cut -c1-300
 done
 python - <<PY
 import json
-for v in ("default", "PACK_HW", "POLL_CTA0", "WEAK_LOADS"):
+for v in ("default", "PACK_HW", "POLL_CTA0", "WEAK_LOADS", "NO_EXTRA_FENCE"):
     try:
         d = json.load(open("$OUT/fake8_%s.json" % v))
     except Exception as e:

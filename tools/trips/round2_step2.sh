@@ -7,7 +7,7 @@ N=${1:-2}
 OUT=gpurun_out/r2_step2_n$N; mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 port=29950
-for v in default PACK_HW POLL_CTA0 WEAK_LOADS; do
+for v in default PACK_HW POLL_CTA0 WEAK_LOADS NO_EXTRA_FENCE; do
   port=$((port + 1))
   echo "== variant $v: check + sweep"
   env $( [ $v = default ] && echo X=1 || echo CPD_B200_$v=1 ) timeout 420 $TR --master-port $port tools/multigpu_check.py --specials --sections correct,sweep \
@@ -16,7 +16,7 @@ for v in default PACK_HW POLL_CTA0 WEAK_LOADS; do
 done
 python - <<PY
 import json
-for v in ("default", "PACK_HW", "POLL_CTA0", "WEAK_LOADS"):
+for v in ("default", "PACK_HW", "POLL_CTA0", "WEAK_LOADS", "NO_EXTRA_FENCE"):
     try:
         d = json.load(open("$OUT/check_sweep_%s.json" % v))
     except Exception as e:
