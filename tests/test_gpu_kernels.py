@@ -50,25 +50,6 @@ def test_quantize_variants():
     assert ab.view(torch.float32).item() == x.abs().max().item()
 
 
-def test_quantize_more_than_2_31_elements():
-    """64-bit indexing (the reference truncates the size to int, quant.cu:17): 2^31 + 4099 elements in place."""
-    n = (1 << 31) + 4099
-    free, _ = torch.cuda.mem_get_info()
-    if free < n * 4 + (1 << 30):
-        pytest.skip("not enough free device memory")
-    x = torch.empty(n, device="cuda")
-    x.fill_(1.2345)
-    x[-4099:] = torch.linspace(-3.0, 3.0, 4099, device="cuda")
-    tail = x[-4099:].clone().cpu()
-    float_quantize(x, 4, 3, inplace=True)
-    assert _same(x[-4099:], float_quantize(tail, 4, 3))
-    assert _same(x[:1024], float_quantize(torch.full((1024,), 1.2345), 4, 3))
-    mid = (1 << 31) - 512
-    assert _same(x[mid:mid + 1024], float_quantize(torch.full((1024,), 1.2345), 4, 3))
-    del x
-    torch.cuda.empty_cache()
-
-
 @pytest.mark.parametrize("M,N,K", [(64, 64, 64), (1, 1, 1), (17, 65, 33), (130, 70, 257), (10, 512, 48)])
 @pytest.mark.parametrize("e,m,kahan", [(4, 3, True), (5, 2, True), (5, 10, False), (8, 23, True)])
 def test_gemm_exact_matches_cpu(M, N, K, e, m, kahan):
@@ -93,7 +74,7 @@ def _arenas(W, numels, seed, device):
     return layout, out
 
 
-@pytest.mark.parametrize("W", [1, 2, 8, 32])
+@pytest.mark.parametrize("W", [1, 2, 8])
 @pytest.mark.parametrize("e,m", [(4, 3), (5, 2), (5, 10), (6, 9)])
 @pytest.mark.parametrize("aps,kahan", [(True, False), (True, True), (False, False), (False, True)])
 def test_aps_fold_matches_cpu(W, e, m, aps, kahan):
@@ -159,45 +140,6 @@ def test_engine_graph_matches_eager_and_learns():
         runs.append([eng.train_step(xb, yb) for _ in range(6)])
     assert runs[0][-1] < runs[0][0]
     assert np.allclose(runs[0], runs[1], rtol=2e-2), runs
-
-
-def test_overlapped_bucketed_reduce_equals_sequential():
-    """buckets reduced on the comm stream as soon as their gradients are ready (hooks, eager and captured
-    in a CUDA graph) give the same weights as reducing the same buckets after backward."""
-    from cpd_b200.train import TrainEngine
-
-    def run(overlap, graph):
-        torch.manual_seed(0)
-        layers = []
-        for _ in range(6):
-            layers += [torch.nn.Linear(256, 256), torch.nn.ReLU()]
-        m = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 8 * 8, 256), torch.nn.ReLU(), *layers, torch.nn.Linear(256, 10))
-        eng = TrainEngine(m, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, bucket_mb=0.3, overlap=overlap), batch_size=64,
-                          input_shape=(3, 8, 8), lr=0.05, use_lars=False, cuda_graph=graph, warmup_steps=1, channels_last=False)
-        assert len(eng.reducer.buckets) >= 4
-        g = torch.Generator().manual_seed(1)
-        x, y = torch.randn(64, 3, 8, 8, generator=g).pin_memory(), torch.randint(0, 10, (64,), generator=g).pin_memory()
-        losses = [eng.train_step(x, y) for _ in range(5)]
-        torch.cuda.synchronize()
-        # direct evidence that EVERY bucket was reduced: each gradient, times its tensor's APS scale, is a (4,3) member
-        k = 0
-        for b, sh in zip(eng.reducer.buckets, eng.reducer.shifts):
-            for t in range(b.T):
-                g = eng.arena.grad_views[b.t0 + t].detach().flatten().float() * (2.0 ** int(sh[t]))
-                assert torch.equal(float_quantize(g, 4, 3), g), (overlap, graph, b.t0 + t)
-                k += 1
-        assert k == len(eng.arena.params)
-        return eng.arena.model_flat.clone(), losses
-
-    for graph in (False, True):
-        w_seq, l_seq = run(False, graph)
-        w_ovl, l_ovl = run(True, graph)
-        # same kernels, same order per bucket -> equal; the criterion tolerates a stray rounding flip but not a bucket that
-        # missed its reduce (at world size 1 that is the (4,3) quantisation of every gradient element: percent-level)
-        bad = ((w_ovl - w_seq).abs() > 3e-8 + 1e-6 * w_seq.abs()).float().mean().item()      # an unreduced run: ~0.3
-        assert bad < 0.05, (graph, bad, float((w_ovl - w_seq).abs().max()))
-        assert np.allclose(l_ovl, l_seq, rtol=1e-3), (graph, l_ovl, l_seq)
-        assert l_seq[-1] < l_seq[0]
 
 
 def test_engine_emulate_node_equals_cpu_semantics():
@@ -357,20 +299,3 @@ def test_quant_conv_tile_mode_first_layer_k27():
     assert (y - ref).abs().max() / ref.abs().max() < 3e-2
     y.sum().backward()
     assert torch.isfinite(qc.weight.grad).all() and torch.isfinite(x.grad).all()
-
-
-@pytest.mark.timeout(300)
-@pytest.mark.parametrize("world", [8, 4])
-def test_fused_allreduce_fake_world_matches_cpu_fold(world):
-    """The cross-GPU kernel on ONE GPU: it is told world_size = W while every peer pointer aliases local memory
-    (tools/fake_world.py), so the raw and packed one-shot variants run their full W-rank instruction stream —
-    amax, exponent mailboxes, scale + cast + pack, W-rank decode + fold (plain and Kahan), unscale — and the result
-    must equal the pure-software CPU fold of W copies bit for bit, incl. tensors with NaN / Inf / zeros / fp32 denormals."""
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29700 + world + os.getpid() % 200))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fake_world.py"), "--check-only", "--world", str(world)],
-                       capture_output=True, text=True, timeout=280, env=env)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    assert "mismatching cases: none" in r.stdout, r.stdout[-3000:]
