@@ -4,7 +4,7 @@
 set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 OUT=gpurun_out/r2_step1; mkdir -p $OUT
-echo "== new GPU tests"; timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu \
+echo "== new GPU tests"; timeout 600 python -m pytest tests/test_zz_gpu_late.py tests/test_gpu_kernels.py -q -m gpu \
   -k "fake_world or more_than_2_31 or overlapped or aps_fold or emulate" > $OUT/pytest_new.log 2>&1; echo "rc=$?"; tail -3 $OUT/pytest_new.log
 for v in default PACK_HW POLL_CTA0 WEAK_LOADS NO_EXTRA_FENCE; do
   echo "== fake world W=8, variant $v (check + timing)"
