@@ -60,7 +60,7 @@ constexpr int kMaxLocalSources = 64;
 //   srcs: device array of W pointers to flat fp32 arenas sharing the chunk table
 //   workspace: 4 + 2*T_cap unsigned (grid barrier, launch counter, amax[2][T_cap]), zeroed once
 void aps_fold_local_cuda(const float* const* srcs, int W, float* out, const Chunk* chunks,
-                         int n_chunks, int T, int T_cap, int e, int m, bool use_aps, bool kahan,
+                         int n_chunks, int T, int T_cap, int e, int m, int rounding, bool use_aps, bool kahan,
                          float world_mult, unsigned* workspace, int* shifts_out, int max_ctas,
                          cudaStream_t st);
 
@@ -79,12 +79,18 @@ struct CommBuffers {
   float* mailbox[16];          // APS exponents  [2 parities][8 source ranks][max_tensors] (pushed by the sources)
   unsigned* flags[16];         // signal pad     [3][16] epoch flags per phase
   unsigned char* mc_gather;    // multicast view of `gather` (nullptr when no NVLS)
+  unsigned char* mc_data;      // multicast view of `data` (in-switch reductions: multimem.ld_reduce)
   size_t cap_bytes;
   int max_tensors;
 };
-enum AllreduceAlgo : int { ALGO_AUTO = 0, ALGO_ONESHOT = 1, ALGO_TWOSHOT = 2, ALGO_NVLS = 3, ALGO_ONESHOT_RAW = 4 };
+// ALGO_NVLS_SUM: fp32 wire, the whole reduction inside the switch (multimem.ld_reduce.add.f32) - the (8,23) path, whose
+//   reference is a plain NCCL all_reduce (dist_util.py:55-59; summation order unspecified there too).
+// ALGO_NVLS_FAST: fp8 wire codes summed inside the switch with an fp16 accumulator (multimem.ld_reduce ... acc::f16):
+//   explicitly NOT the rank-ordered CPD fold (one rounding at the end instead of one per add) - opt-in only.
+enum AllreduceAlgo : int { ALGO_AUTO = 0, ALGO_ONESHOT = 1, ALGO_TWOSHOT = 2, ALGO_NVLS = 3, ALGO_ONESHOT_RAW = 4,
+                           ALGO_NVLS_SUM = 5, ALGO_NVLS_FAST = 6 };
 void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunks, int n_chunks,
-                          int T, int e, int m, bool use_aps, bool kahan, int algo, bool prequant, int wire,
+                          int T, int e, int m, int rounding, bool use_aps, bool kahan, int algo, bool prequant, int wire,
                           unsigned* local_ws /*barrier[2], epoch, status, amax[2][T]*/, int* shifts_out,
                           int max_ctas, unsigned long long timeout_cycles, cudaStream_t st);
 

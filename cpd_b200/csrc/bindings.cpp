@@ -100,22 +100,22 @@ PYBIND11_MODULE(_C, m) {
   });
 
   // --------------------------------------------------------- multi-tensor arenas --
-  m.def("aps_fold_cpu", [](std::vector<uptr> srcs, uptr out, uptr seg_off, int T, int e, int mb, bool use_aps, bool kahan,
+  m.def("aps_fold_cpu", [](std::vector<uptr> srcs, uptr out, uptr seg_off, int T, int e, int mb, int rounding, bool use_aps, bool kahan,
                            double world_mult, uptr shifts_out) {
     check_fmt(e, mb);
     std::vector<const float*> ptrs;
     for (auto s : srcs) ptrs.push_back(P<const float>(s));
     py::gil_scoped_release nogil;
-    cpd::aps_fold_cpu(ptrs.data(), (int)ptrs.size(), P<float>(out), P<const int64_t>(seg_off), T, e, mb, cpd::ROUND_REF, use_aps,
+    cpd::aps_fold_cpu(ptrs.data(), (int)ptrs.size(), P<float>(out), P<const int64_t>(seg_off), T, e, mb, rounding, use_aps,
                       kahan, (float)world_mult, P<int>(shifts_out));
   });
-  m.def("aps_fold_cuda", [](std::vector<uptr> srcs, uptr out, uptr chunks, int n_chunks, int T, int T_cap, int e, int mb, bool use_aps,
-                            bool kahan, double world_mult, uptr workspace, uptr shifts_out, int max_ctas, uptr stream) {
+  m.def("aps_fold_cuda", [](std::vector<uptr> srcs, uptr out, uptr chunks, int n_chunks, int T, int T_cap, int e, int mb, int rounding,
+                            bool use_aps, bool kahan, double world_mult, uptr workspace, uptr shifts_out, int max_ctas, uptr stream) {
     check_fmt(e, mb);
     if (srcs.empty() || srcs.size() > (size_t)cpd::kMaxLocalSources) throw std::invalid_argument("aps_fold: 1..64 sources");
     std::vector<const float*> ptrs;
     for (auto s : srcs) ptrs.push_back(P<const float>(s));
-    cpd::aps_fold_local_cuda(ptrs.data(), (int)ptrs.size(), P<float>(out), P<const cpd::Chunk>(chunks), n_chunks, T, T_cap, e, mb, use_aps,
+    cpd::aps_fold_local_cuda(ptrs.data(), (int)ptrs.size(), P<float>(out), P<const cpd::Chunk>(chunks), n_chunks, T, T_cap, e, mb, rounding, use_aps,
                              kahan, (float)world_mult, P<unsigned>(workspace), P<int>(shifts_out), max_ctas, S(stream));
     check_launch("aps_fold");
   });
@@ -166,7 +166,7 @@ PYBIND11_MODULE(_C, m) {
 
   py::class_<PyCommBuffers>(m, "CommBuffers")
       .def(py::init([](int rank, int world, std::vector<uptr> data, std::vector<uptr> gather, std::vector<uptr> mailbox,
-                       std::vector<uptr> flags, uptr mc_gather, size_t cap_bytes, int max_tensors) {
+                       std::vector<uptr> flags, uptr mc_gather, size_t cap_bytes, int max_tensors, uptr mc_data) {
         if (world < 1 || world > 8) throw std::invalid_argument("fused all-reduce supports 1..8 ranks per node");
         if ((int)data.size() != world || (int)gather.size() != world || (int)mailbox.size() != world || (int)flags.size() != world)
           throw std::invalid_argument("CommBuffers: need one pointer per rank");
@@ -180,24 +180,30 @@ PYBIND11_MODULE(_C, m) {
           b.cb.flags[r] = P<unsigned>(flags[r]);
         }
         b.cb.mc_gather = P<unsigned char>(mc_gather);
+        b.cb.mc_data = P<unsigned char>(mc_data);
         b.cb.cap_bytes = cap_bytes;
         b.cb.max_tensors = max_tensors;
         return b;
-      }))
+      }), py::arg("rank"), py::arg("world"), py::arg("data"), py::arg("gather"), py::arg("mailbox"), py::arg("flags"),
+         py::arg("mc_gather"), py::arg("cap_bytes"), py::arg("max_tensors"), py::arg("mc_data") = (uptr)0)
       .def_property_readonly("cap_bytes", [](const PyCommBuffers& b) { return b.cb.cap_bytes; })
       .def_property_readonly("max_tensors", [](const PyCommBuffers& b) { return b.cb.max_tensors; })
       .def_property_readonly("has_multicast", [](const PyCommBuffers& b) { return b.cb.mc_gather != nullptr; });
 
   m.def("allreduce_fused_cuda", [](const PyCommBuffers& b, uptr grad, int64_t numel, uptr chunks, int n_chunks, int T, int e, int mb,
-                                   bool use_aps, bool kahan, int algo, bool prequant, int wire, uptr local_ws, uptr shifts_out,
+                                   int rounding, bool use_aps, bool kahan, int algo, bool prequant, int wire, uptr local_ws, uptr shifts_out,
                                    int max_ctas, uint64_t timeout_cycles, uptr stream) {
     check_fmt(e, mb);
     if (T > 1024) throw std::invalid_argument("at most 1024 tensors per bucket");
     if (T > b.cb.max_tensors) throw std::invalid_argument("bucket has more tensors than the mailbox holds");
     if (wire != 8 && wire != 16 && wire != 32) throw std::invalid_argument("wire must be 8, 16 or 32");
-    if ((size_t)numel * (size_t)(algo == cpd::ALGO_ONESHOT_RAW ? 4 : wire / 8) > b.cb.cap_bytes)
+    const int base_algo = algo & 0xFF;           // the upper bits carry opt-in protocol switches
+    const bool fp32_wire = base_algo == cpd::ALGO_ONESHOT_RAW || base_algo == cpd::ALGO_NVLS_SUM;
+    if ((size_t)numel * (size_t)(fp32_wire ? 4 : wire / 8) > b.cb.cap_bytes)
       throw std::invalid_argument("bucket larger than the symmetric wire buffer");
-    cpd::allreduce_fused_cuda(b.cb, P<float>(grad), P<const cpd::Chunk>(chunks), n_chunks, T, e, mb, use_aps, kahan, algo, prequant,
+    if (n_chunks < 0 || (int64_t)n_chunks * 4096 < numel)
+      throw std::invalid_argument("chunk table does not cover the bucket");
+    cpd::allreduce_fused_cuda(b.cb, P<float>(grad), P<const cpd::Chunk>(chunks), n_chunks, T, e, mb, rounding, use_aps, kahan, algo, prequant,
                               wire, P<unsigned>(local_ws), P<int>(shifts_out), max_ctas, timeout_cycles, S(stream));
     check_launch("allreduce_fused");
   });

@@ -73,6 +73,25 @@ __device__ __forceinline__ float4 multimem_ld_reduce_add_f4(const void* mc) {
   return r;
 }
 
+__device__ __forceinline__ void multimem_st_f4(void* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// in-switch sum of the 16 fp8 codes at the same address on every GPU, accumulated in fp16 inside the switch and rounded
+// back to fp8 codes once (LDGMC.E.HPADD.E4M3x16 / E5M2x16): ONE rounding per element instead of the CPD fold's one per
+// add - the explicitly non-bit-exact "nvls_fast" mode
+template <bool E5M2>
+__device__ __forceinline__ uint4 multimem_ld_reduce_add_fp8x16(const void* mc) {
+  uint4 r;
+  if (E5M2)
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f16.v4.e5m2x4 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(mc) : "memory");
+  else
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f16.v4.e4m3x4 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(mc) : "memory");
+  return r;
+}
+
 // ---- flags -------------------------------------------------------------------
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");

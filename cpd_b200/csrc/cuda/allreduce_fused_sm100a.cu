@@ -44,6 +44,7 @@ struct ArParams {
   float* mailbox[kArMaxW];
   unsigned* flags[kArMaxW];
   unsigned char* mc_gather;
+  unsigned char* mc_data;
   long long cap_bytes;
   int max_tensors;
   float* grad;
@@ -58,6 +59,9 @@ struct ArParams {
   int* shifts_out;
   unsigned long long timeout;
 };
+
+template <class F> struct IsE5M2 { static constexpr bool value = false; };
+template <> struct IsE5M2<FmtT<5, 2>> { static constexpr bool value = true; };
 
 // ---- wire granule (16 elements) load / store / codec ------------------------------
 template <int WIRE> struct Granule;
@@ -176,7 +180,11 @@ __device__ __forceinline__ void signal_peers(const ArParams& p, int phase, unsig
 // Default: W threads of EVERY CTA poll the peers' flags.  Opt-in (poll_cta0, algo bit 9): only CTA 0 polls the line
 // the peers' release-stores land in and republishes a local go-flag (release/acquire at gpu scope) that the other
 // CTAs poll - 296 x W pollers no longer compete with the incoming NVLink writes for that one L2 line.
-__device__ __forceinline__ void wait_peers(const ArParams& p, int phase, unsigned epoch) {
+// Returns true (CTA-uniform) when the wait timed out - now or in an earlier launch whose status the host has not
+// cleared yet: the caller then POISONS its outputs (NaN) instead of folding stale peer data into the gradients, so a
+// straggler can never silently corrupt a step (NCCL would have blocked; we fail loudly and bounded).
+__device__ __forceinline__ bool wait_peers(const ArParams& p, int phase, unsigned epoch) {
+  __shared__ unsigned s_bad;
   unsigned* go = p.ws + 4 + 2 * p.max_tensors + 26 + phase;
   if (!p.poll_cta0 || blockIdx.x == 0) {
     if (threadIdx.x < p.world) {
@@ -196,10 +204,16 @@ __device__ __forceinline__ void wait_peers(const ArParams& p, int phase, unsigne
   } else if (threadIdx.x == 0) {
     const long long t0 = clock64();
     while ((int)(ld_acquire_gpu(go) - epoch) < 0) {
-      if ((unsigned long long)(clock64() - t0) > 2 * p.timeout) break;      // CTA 0 reports the missing peer
+      if ((unsigned long long)(clock64() - t0) > 2 * p.timeout) {              // CTA 0 reports the missing peer
+        atomicOr(&p.ws[3], 0x80000000u);
+        break;
+      }
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0) s_bad = ld_acquire_gpu(&p.ws[3]) & 0x80000000u;
+  __syncthreads();
+  return s_bad != 0u;
 }
 
 // phase timestamps (ns, %globaltimer) of CTA 0 for attribution: ws tail, 8 x u64 after the amax buffers
@@ -240,6 +254,8 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
   unsigned* amax = p.ws + 4 + par * p.max_tensors;
   unsigned char* my_data = p.data[rank] + par * p.cap_bytes;
 
+  bool poison = false;                 // set when a peer never showed up: outputs become NaN (see wait_peers)
+  const float kPoison = __int_as_float(0x7FC00000);
   stamp(p, 0);
   // ---------------- single-round variant for small buckets (ALGO_ONESHOT_RAW) ---------------------------
   // Latency-bound messages: ONE flag round instead of two.  Each rank publishes its RAW fp32 gradients plus
@@ -278,7 +294,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
       __syncthreads();
     }
     signal_peers(p, 1, epoch);
-    wait_peers(p, 1, epoch);
+    poison |= wait_peers(p, 1, epoch);
     stamp(p, 4);
     for (int t = threadIdx.x; t < p.T; t += kArThreads) {
       float me = -INFINITY;
@@ -296,7 +312,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
     for (int w = blockIdx.x; w < 4 * p.n_chunks; w += gridDim.x) {
       const Chunk ck = p.chunks[w >> 2];
       const int sh = s_shift[ck.tensor];
-      const float sc = pow2i(sh), inv = pow2i(-sh);
+      const float sc = pow2i(sh), inv = poison ? kPoison : pow2i(-sh);
       // all W peers' vectors requested before the first use
       for (int v4 = (w & 3) * kArThreads + threadIdx.x; v4 < (ck.len >> 2); v4 += 4 * kArThreads) {
         const long long e0 = ck.start + 4 * v4;
@@ -319,6 +335,52 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
           }
         }
         *reinterpret_cast<float4*>(p.grad + e0) = make_float4(s4[0] * inv, s4[1] * inv, s4[2] * inv, s4[3] * inv);
+      }
+    }
+    stamp(p, 7);
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.ws[2] = epoch;
+    return;
+  }
+
+  // ---------------- in-switch fp32 sum (ALGO_NVLS_SUM): the (8,23) path ---------------------------------------
+  // Reference: plain NCCL all_reduce per parameter (dist_util.py:55-59).  Here: every rank publishes its fp32
+  // gradients in the symmetric buffer; the owner of a chunk issues ONE multimem.ld_reduce.add.v4.f32 per 16 bytes -
+  // the NVSwitch adds the W replicas - and ONE multimem.st broadcasts the sum into every rank's buffer; each rank
+  // then copies its buffer back.  2(W-1)/W * 4 B per element cross the links, the SMs never fold.  All ranks receive
+  // the same bits (one reducer per element); the summation order is the switch's, as NCCL's is NCCL's.
+  if (WIRE == 32 && p.algo == ALGO_NVLS_SUM) {
+    float* my_raw = reinterpret_cast<float*>(my_data);
+    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
+      const Chunk ck = p.chunks[c];
+      for (int v4 = threadIdx.x; v4 < (ck.len >> 2); v4 += kArThreads)
+        st_f4(my_raw + ck.start + 4 * v4, ld_stream_f4(p.grad + ck.start + 4 * v4));
+    }
+    grid_barrier(bar);
+    stamp(p, 3);
+    signal_peers(p, 1, epoch);
+    poison |= wait_peers(p, 1, epoch);
+    stamp(p, 4);
+    float* mc = reinterpret_cast<float*>(p.mc_data + par * p.cap_bytes);
+    for (int c = rank + W * (int)blockIdx.x; c < p.n_chunks; c += W * (int)gridDim.x) {
+      const Chunk ck = p.chunks[c];
+      for (int v4 = threadIdx.x; v4 < (ck.len >> 2); v4 += kArThreads) {
+        float4 r = multimem_ld_reduce_add_f4(mc + ck.start + 4 * v4);
+        if (poison) r = make_float4(kPoison, kPoison, kPoison, kPoison);
+        multimem_st_f4(mc + ck.start + 4 * v4, r);
+      }
+    }
+    stamp(p, 5);
+    grid_barrier(bar);
+    signal_peers(p, 2, epoch);
+    poison |= wait_peers(p, 2, epoch);
+    stamp(p, 6);
+    for (int c = blockIdx.x; c < p.n_chunks; c += gridDim.x) {
+      const Chunk ck = p.chunks[c];
+      for (int v4 = threadIdx.x; v4 < (ck.len >> 2); v4 += kArThreads) {
+        const uint4 u = ld_sys_u4(my_raw + ck.start + 4 * v4);
+        float4 r = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+        if (poison) r = make_float4(kPoison, kPoison, kPoison, kPoison);
+        st_f4(p.grad + ck.start + 4 * v4, r);
       }
     }
     stamp(p, 7);
@@ -396,7 +458,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
       __syncthreads();
     }
     signal_peers(p, 0, epoch);
-    wait_peers(p, 0, epoch);
+    poison |= wait_peers(p, 0, epoch);
     for (int t = threadIdx.x; t < p.T; t += kArThreads) {
       float me = -INFINITY;
       for (int r = 0; r < W; ++r) {
@@ -434,16 +496,19 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
   grid_barrier(bar);
   stamp(p, 3);
   signal_peers(p, 1, epoch);
-  wait_peers(p, 1, epoch);
+  poison |= wait_peers(p, 1, epoch);
   stamp(p, 4);
 
   // ---------------- phase C: rank-ordered quantised fold over peer memory ----------
   const bool two_shot = p.algo != ALGO_ONESHOT;
+  // opt-in, NOT the CPD fold: the switch sums the W ranks' fp8 codes with an fp16 accumulator and rounds once
+  // (ALGO_NVLS_FAST); everything around it (APS exponents, pack, gather, unscale) is the exact path's
+  const bool nvls_fast = WIRE == 8 && FoldOps<F>::kHw && p.algo == ALGO_NVLS_FAST;
   const int c_begin = two_shot ? rank + W * (int)blockIdx.x : (int)blockIdx.x;
   const int c_step = two_shot ? W * (int)gridDim.x : (int)gridDim.x;
   for (int c = c_begin; c < p.n_chunks; c += c_step) {
     const Chunk ck = p.chunks[c];
-    const float inv = p.use_aps ? pow2i(-s_shift[ck.tensor]) : 1.f;
+    const float inv = poison ? kPoison : (p.use_aps ? pow2i(-s_shift[ck.tensor]) : 1.f);
     for (int g = threadIdx.x; g < (ck.len >> 4); g += kArThreads) {
       const long long e0 = ck.start + 16 * g;
       const bool first = c == c_begin && g == (int)threadIdx.x;      // finer stamps of CTA 0's first granule (slots 9..12)
@@ -452,6 +517,12 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
       // per thread hides the ~2 us NVLink latency); fp32 wire loads rank by rank.
       constexpr int kPre = WIRE <= 16 ? kArMaxW : 1;
       Granule<WIRE> in[kPre];
+      float s[16], cc[16];
+      if (nvls_fast) {
+        Granule<WIRE> sum;
+        sum.v[0] = multimem_ld_reduce_add_fp8x16<IsE5M2<F>::value>(p.mc_data + par * p.cap_bytes + e0);
+        granule_decode<WIRE>(fmt, sum, s);
+      } else {
       if (WIRE <= 16) {
 #pragma unroll
         for (int r = 0; r < kPre; ++r)
@@ -466,7 +537,6 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
         asm volatile("" :: "r"(acc));                                   // all peer vectors have landed
         stamp(p, 10);
       }
-      float s[16], cc[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) { s[i] = 0.f; cc[i] = 0.f; }
       // the rank loop is not unrolled: the loads above are all in flight already, and 8 unrolled copies of decode +
@@ -491,10 +561,15 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
           }
         }
       }
+      }  // !nvls_fast
       if (first) stamp(p, 11);
+      if (poison) {                                     // also what travels to the peers in the gather half
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s[i] = kPoison;
+      }
       if (two_shot) {
         const Granule<WIRE> out = granule_encode<WIRE>(fmt, s);
-        if (p.algo == ALGO_NVLS && p.mc_gather) {
+        if ((p.algo == ALGO_NVLS || p.algo == ALGO_NVLS_FAST) && p.mc_gather) {
           granule_store_mc<WIRE>(p.mc_gather + par * p.cap_bytes, e0, out);
         } else {
 #pragma unroll
@@ -502,7 +577,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
             if (r < W && r != rank) granule_store<WIRE>(p.gather[r] + par * p.cap_bytes, e0, out, true);
         }
       }
-      if (p.use_aps) {
+      if (p.use_aps || poison) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) s[i] *= inv;
       }
@@ -516,7 +591,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
   if (two_shot) {
     grid_barrier(bar);
     signal_peers(p, 2, epoch);
-    wait_peers(p, 2, epoch);
+    poison |= wait_peers(p, 2, epoch);
     stamp(p, 6);
     const unsigned char* my_gather = p.gather[rank] + par * p.cap_bytes;
     for (int c = blockIdx.x; c < p.n_chunks; c += 2 * gridDim.x) {
@@ -530,20 +605,20 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
       if (a0) in0 = granule_load_sys<WIRE>(my_gather, e0);
       if (a1) in1 = granule_load_sys<WIRE>(my_gather, e1);
       if (a0) {
-        const float inv = p.use_aps ? pow2i(-s_shift[ck0.tensor]) : 1.f;
+        const float inv = poison ? kPoison : (p.use_aps ? pow2i(-s_shift[ck0.tensor]) : 1.f);
         float v[16];
         granule_decode<WIRE>(fmt, in0, v);
-        if (p.use_aps) {
+        if (p.use_aps || poison) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= inv;
         }
         store16(p.grad + e0, v);
       }
       if (a1) {
-        const float inv = p.use_aps ? pow2i(-s_shift[ck1.tensor]) : 1.f;
+        const float inv = poison ? kPoison : (p.use_aps ? pow2i(-s_shift[ck1.tensor]) : 1.f);
         float v[16];
         granule_decode<WIRE>(fmt, in1, v);
-        if (p.use_aps) {
+        if (p.use_aps || poison) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= inv;
         }
@@ -557,7 +632,7 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
 }
 
 void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunks, int n_chunks, int T,
-                          int e, int m, bool use_aps, bool kahan, int algo, bool prequant, int wire,
+                          int e, int m, int rounding, bool use_aps, bool kahan, int algo, bool prequant, int wire,
                           unsigned* local_ws, int* shifts_out, int max_ctas, unsigned long long timeout_cycles,
                           cudaStream_t st) {
   if (n_chunks <= 0) return;
@@ -570,6 +645,7 @@ void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunk
     p.flags[r] = r < cb.world ? cb.flags[r] : nullptr;
   }
   p.mc_gather = cb.mc_gather;
+  p.mc_data = cb.mc_data;
   p.cap_bytes = (long long)cb.cap_bytes;
   p.max_tensors = cb.max_tensors;
   p.grad = grad; p.chunks = chunks; p.n_chunks = n_chunks; p.T = T;
@@ -580,12 +656,19 @@ void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunk
   p.no_extra_fence = (algo >> 11) & 1;
   p.ident = (e == 8 && m == 23 && !kahan) ? 1 : 0;
   p.ws = local_ws; p.shifts_out = shifts_out; p.timeout = timeout_cycles;
+  const bool fp8_hw = rounding == ROUND_REF && wire == 8 && ((e == 4 && m == 3) || (e == 5 && m == 2));
+  if (p.algo == ALGO_NVLS_SUM && !(p.ident && !use_aps && wire == 32 && cb.mc_data)) p.algo = ALGO_TWOSHOT;
+  if (p.algo == ALGO_NVLS_FAST && !(fp8_hw && use_aps && cb.mc_data && cb.mc_gather)) p.algo = ALGO_NVLS;
   if (p.algo == ALGO_NVLS && !cb.mc_gather) p.algo = ALGO_TWOSHOT;
   if (p.algo == ALGO_ONESHOT_RAW && !use_aps) p.algo = ALGO_ONESHOT;     // without APS the fp32-wire one-shot already needs one round
   // two co-resident CTAs per SM (<= 128 registers by launch bounds): 16 warps / SM keep enough 128-bit
-  // loads in flight to cover HBM / NVLink latency; the grid barrier needs all CTAs resident
+  // loads in flight to cover HBM / NVLink latency; the grid barrier needs all CTAs resident.  A caller that
+  // overlaps the reduction with other kernels passes a small max_ctas (8..32) so the comm grid co-runs with them.
   int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1) * 2;
-  if (grid > n_chunks) grid = n_chunks;
+  // work items: whole chunks, except the single-round raw variant whose fold is scheduled in quarter chunks (one
+  // 16-byte vector per thread = one peer round trip per thread)
+  const int items = p.algo == ALGO_ONESHOT_RAW ? 4 * n_chunks : n_chunks;
+  if (grid > items) grid = items;
 
 #define CPD_AR_LAUNCH(WIRE_)                                                                          \
   do {                                                                                                \
@@ -593,14 +676,15 @@ void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunk
     else allreduce_fused_kernel<decltype(FMT), WIRE_, false><<<grid, kArThreads, 0, st>>>(p, FMT);      \
   } while (0)
 
-  // compile-time formats carry their natural wire width; everything else goes through the
+  // compile-time formats carry their natural wire width; everything else (and IEEE rounding) goes through the
   // runtime codec at the requested width
-  if (wire == 8 && e == 4 && m == 3) { FmtT<4, 3> FMT; CPD_AR_LAUNCH(8); }
-  else if (wire == 8 && e == 5 && m == 2) { FmtT<5, 2> FMT; CPD_AR_LAUNCH(8); }
-  else if (wire == 16 && e == 5 && m == 10) { FmtT<5, 10> FMT; CPD_AR_LAUNCH(16); }
-  else if (wire == 16 && e == 8 && m == 7) { FmtT<8, 7> FMT; CPD_AR_LAUNCH(16); }
+  const bool ref = rounding == ROUND_REF;
+  if (ref && wire == 8 && e == 4 && m == 3) { FmtT<4, 3> FMT; CPD_AR_LAUNCH(8); }
+  else if (ref && wire == 8 && e == 5 && m == 2) { FmtT<5, 2> FMT; CPD_AR_LAUNCH(8); }
+  else if (ref && wire == 16 && e == 5 && m == 10) { FmtT<5, 10> FMT; CPD_AR_LAUNCH(16); }
+  else if (ref && wire == 16 && e == 8 && m == 7) { FmtT<8, 7> FMT; CPD_AR_LAUNCH(16); }
   else {
-    FmtR FMT{make_format(e, m, ROUND_REF)};
+    FmtR FMT{make_format(e, m, rounding)};
     if (wire == 8) CPD_AR_LAUNCH(8);
     else if (wire == 16) CPD_AR_LAUNCH(16);
     else CPD_AR_LAUNCH(32);

@@ -135,14 +135,14 @@ aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__
 }
 
 void aps_fold_local_cuda(const float* const* srcs_host, int W, float* out, const Chunk* chunks,
-                         int n_chunks, int T, int T_cap, int e, int m, bool use_aps, bool kahan, float world_mult,
+                         int n_chunks, int T, int T_cap, int e, int m, int rounding, bool use_aps, bool kahan, float world_mult,
                          unsigned* workspace, int* shifts_out, int max_ctas, cudaStream_t st) {
   if (n_chunks <= 0 || W <= 0) return;
   SrcPtrs sp;
   for (int r = 0; r < kMaxLocalSrc; ++r) sp.p[r] = r < W ? srcs_host[r] : nullptr;
   int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1) * 4;   // 4 co-resident CTAs / SM (launch bounds)
   if (grid > n_chunks) grid = n_chunks;
-  CPD_DISPATCH_FORMAT(e, m, ROUND_REF, FMT, {
+  CPD_DISPATCH_FORMAT(e, m, rounding, FMT, {
     if (kahan)
       aps_fold_local_kernel<decltype(FMT), true><<<grid, kFoldThreads, 0, st>>>(
           sp, W, out, chunks, n_chunks, T, T_cap, FMT, use_aps, world_mult, workspace, shifts_out);

@@ -24,7 +24,7 @@ ALIGN_ELEMS = 16            # tensors start on 64-byte boundaries inside an aren
 CHUNK_DTYPE = np.dtype([("start", "<i8"), ("len", "<i4"), ("tensor", "<i4")])
 assert CHUNK_DTYPE.itemsize == _C.chunk_struct_size()
 
-ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_ONESHOT_RAW = 0, 1, 2, 3, 4
+ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_ONESHOT_RAW, ALGO_NVLS_SUM, ALGO_NVLS_FAST = 0, 1, 2, 3, 4, 5, 6
 
 
 def rounding_code(rounding) -> int:
@@ -220,9 +220,10 @@ def gemm_tc_mx(a_codes, a_sf, bt_codes, bt_sf, exp: int, man: int, kahan: bool =
 def aps_fold(srcs: Sequence[torch.Tensor], out: torch.Tensor, seg_off: torch.Tensor, exp: int, man: int,
              use_aps: bool, kahan: bool, world_mult: float, chunks: Optional[torch.Tensor] = None,
              workspace: Optional[torch.Tensor] = None, shifts_out: Optional[torch.Tensor] = None,
-             max_ctas: int = 0) -> torch.Tensor:
+             max_ctas: int = 0, rounding=ROUND_REF) -> torch.Tensor:
     """APS + rank-ordered (Kahan) quantised fold over len(srcs) flat arenas -> out."""
     _check_fmt(exp, man)
+    r = rounding_code(rounding)
     for s in srcs:
         _f32(s, "src")
         if not s.is_contiguous() or s.numel() != out.numel() or s.device != out.device:
@@ -240,12 +241,12 @@ def aps_fold(srcs: Sequence[torch.Tensor], out: torch.Tensor, seg_off: torch.Ten
         n_chunks = chunks.numel() // CHUNK_DTYPE.itemsize
         with torch.cuda.device(out.device):
             _C.aps_fold_cuda([s.data_ptr() for s in srcs], out.data_ptr(), chunks.data_ptr(), n_chunks, T, t_cap, int(exp),
-                             int(man), bool(use_aps), bool(kahan), float(world_mult), workspace.data_ptr(),
+                             int(man), r, bool(use_aps), bool(kahan), float(world_mult), workspace.data_ptr(),
                              _ptr(shifts_out), int(max_ctas), _stream(out))
     else:
         if seg_off.dtype != torch.int64 or seg_off.is_cuda:
             raise ValueError("seg_off: int64 CPU tensor expected")
-        _C.aps_fold_cpu([s.data_ptr() for s in srcs], out.data_ptr(), seg_off.data_ptr(), T, int(exp), int(man),
+        _C.aps_fold_cpu([s.data_ptr() for s in srcs], out.data_ptr(), seg_off.data_ptr(), T, int(exp), int(man), r,
                         bool(use_aps), bool(kahan), float(world_mult), _ptr(shifts_out))
     return out
 

@@ -78,13 +78,37 @@ class FusedSGD:
                 "steps": self.steps, "hyper": dict(momentum=self.momentum, weight_decay=self.weight_decay,
                                                    use_lars=self.use_lars, lars_coeff=self.lars_coeff, nesterov=self.nesterov)}
 
-    def load_state_dict(self, sd: dict) -> None:
-        self.master.copy_(sd["master"])
-        self.mom.copy_(sd["momentum"])
+    def resync_master(self) -> None:
+        """Make the fp32 masters equal to the model arena (after model weights were loaded from a checkpoint that
+        carries no compatible optimizer state: the step copies master -> model, so stale masters would silently
+        revert the load)."""
         if self.model_out is not None:
-            self.model_out.copy_(self.master)
-        self.set_lr(sd.get("lr", self.lr))
-        self.steps = int(sd.get("steps", 0))
+            self.master.copy_(self.arena.model_flat)
+
+    def load_state_dict(self, sd: dict) -> None:
+        """Restore masters + momentum.  Foreign dicts are tolerated: a ``torch.optim.SGD`` state_dict (what the
+        reference trainers save, mix.py:345-356 / main.py:261-269) contributes its momentum buffers and learning
+        rate when the tensor shapes line up, the masters are then re-derived from the (already loaded) model."""
+        if "master" in sd and "momentum" in sd:
+            self.master.copy_(sd["master"])
+            self.mom.copy_(sd["momentum"])
+            if self.model_out is not None:
+                self.model_out.copy_(self.master)
+            self.set_lr(sd.get("lr", self.lr))
+            self.steps = int(sd.get("steps", 0))
+            return
+        self.resync_master()
+        state, groups = sd.get("state"), sd.get("param_groups")
+        if isinstance(state, dict) and isinstance(groups, list):
+            order = [i for g in groups for i in g.get("params", [])]
+            views = [self.arena.layout.view(self.mom, t, like=p.data) for t, p in enumerate(self.arena.params)]
+            if len(order) == len(views):
+                for i, v in zip(order, views):
+                    buf = (state.get(i) or {}).get("momentum_buffer")
+                    if buf is not None and buf.numel() == v.numel():
+                        v.copy_(buf.reshape(v.shape))
+            if groups and "lr" in groups[0]:
+                self.set_lr(float(groups[0]["lr"]))
 
 
 def bn_bias_no_decay(named_params) -> list:

@@ -58,5 +58,5 @@ class EmulateNode:
         cfg = self.cfg
         native.aps_fold(self.slots, self.arena.grad_flat, self.table.seg_off, cfg.grad_exp, cfg.grad_man,
                         cfg.use_aps, False, float(self.E), chunks=self.table.chunks, workspace=self.ws,
-                        shifts_out=self.shifts)
+                        shifts_out=self.shifts, rounding=cfg.rounding)
         self.arena.bind_grads()

@@ -30,30 +30,72 @@ from ..ops import native
 from .arena import ChunkTable, ModelArena
 
 _ALGO = {"auto": native.ALGO_AUTO, "oneshot": native.ALGO_ONESHOT, "twoshot": native.ALGO_TWOSHOT,
-         "nvls": native.ALGO_NVLS, "raw": native.ALGO_ONESHOT_RAW}
+         "nvls": native.ALGO_NVLS, "raw": native.ALGO_ONESHOT_RAW, "nvls_sum": native.ALGO_NVLS_SUM,
+         "nvls_fast": native.ALGO_NVLS_FAST}
 
-# Variant thresholds, from the 8 x B200 sweep with fresh (finite) gradients per call (profiles/allreduce_trip18_n8_*):
-#   fp32 payload      raw    one-shot   two-shot   NVLS    (us, (4,3) + APS, 8-bit wire)
-#   1 KB / 4 KB      21.3 / 21.9   29.1 / 29.3   35.6    35.2
-#   16 KB .. 1 MB    43.6 .. 51.5  30.4 .. 34.7  37.6 .. 39.9
-#   4 MB             78.6    48.4       46.5       45.7
-#   16 MB / 64 MB      -     103.6 / 293   69.7 / 167   67.8 / 166
-# -> raw (one flag round, fp32 on the wire) up to 1 K elements, packed one-shot up to 512 KB of wire codes, NVLS /
-#    two-shot above.  (The raw variant's jump between 4 KB and 16 KB is not understood yet - open item.)
-# opt-in: phase B of the fused kernel packs (4,3)/(5,2) granules with the hardware convert after pretruncate()
-# (algorithm proven against the reference cast on the CPU, tests/cpp; not yet measured on the GPU -> off by default)
-_PACK_HW = 0x100 if os.environ.get("CPD_B200_PACK_HW", "0") == "1" else 0
-# opt-in: only CTA 0 polls the peers' flags and republishes a local go-flag (flag-round contention experiment)
-_PACK_HW |= 0x200 if os.environ.get("CPD_B200_POLL_CTA0", "0") == "1" else 0
-# opt-in: plain loads for the peers' wire data in the fold (do 7 of them overlap better than strong sys-scope loads?)
-_PACK_HW |= 0x400 if os.environ.get("CPD_B200_WEAK_LOADS", "0") == "1" else 0
-# opt-in: drop the explicit system fence in front of the flags' release stores
-_PACK_HW |= 0x800 if os.environ.get("CPD_B200_NO_EXTRA_FENCE", "0") == "1" else 0
+# Protocol switches of the fused kernel (upper bits of the algo word).  The hardware pack (bit 8: scale + reference cast
+# + pack of a granule through pretruncate() + F2FP.SATFINITE, proven equal to the software cast on all 2^32 patterns
+# below the overflow band, tools/exhaustive_cast_check.sh) is ON by default; CPD_B200_PACK_HW=0 switches it off.
+_PROTO = 0x100 if os.environ.get("CPD_B200_PACK_HW", "1") == "1" else 0
+# experiments: only CTA 0 polls the peers' flags / plain loads for the peers' wire data / no extra fence before a flag
+_PROTO |= 0x200 if os.environ.get("CPD_B200_POLL_CTA0", "0") == "1" else 0
+_PROTO |= 0x400 if os.environ.get("CPD_B200_WEAK_LOADS", "0") == "1" else 0
+_PROTO |= 0x800 if os.environ.get("CPD_B200_NO_EXTRA_FENCE", "0") == "1" else 0
 _FAULT_DELAY_RANK = int(os.environ.get("CPD_B200_FAULT_DELAY_RANK", "-1"))
 _FAULT_DELAY_CYCLES = float(os.environ.get("CPD_B200_FAULT_DELAY_CYCLES", "2e8"))
-ONESHOT_MAX_BYTES = 512 * 1024
 MAX_TENSORS_PER_BUCKET = 1024
-RAW_MAX_ELEMS = 1024
+# a peer that does not show up within this many SM cycles (~5 min at 1.9 GHz; NCCL's watchdog default is 10 min) makes
+# the kernel poison its outputs (NaN) and raise the status word; tests shorten it
+DEFAULT_TIMEOUT_CYCLES = 600_000_000_000
+
+
+class Thresholds:
+    """Which fused variant serves which bucket size.  Derived from the discovered topology (per-GPU NVLink bandwidth,
+    multicast) with the latency constants measured on 8 x B200 (profiles/allreduce_*), or overridden by a calibration
+    run on the live process group (``parallel.calibrate``).
+
+    raw (ONE flag round, fp32 on the wire) wins while its extra wire bytes cost less than the second flag round of the
+    packed variants: (W - 1) * 4 B * n / link_bw  <=  t_flag_round.  The packed one-shot ((W - 1) B per element in)
+    hands over to two-shot / NVLS (2 (W - 1) / W B per element) when the byte difference outweighs the third flag
+    round + grid barrier of the gather half."""
+
+    FLAG_ROUND_US = 8.0
+
+    def __init__(self, world: int, link_gbs: float = 900.0, multicast: bool = True, raw_max_elems: Optional[int] = None,
+                 oneshot_max_bytes: Optional[int] = None, source: str = "topology"):
+        self.world, self.link_gbs, self.multicast, self.source = world, float(link_gbs) or 900.0, multicast, source
+        per_us = self.link_gbs * 1e3                      # bytes per microsecond per direction
+        w = max(world, 2)
+        if raw_max_elems is None:
+            raw_max_elems = int(self.FLAG_ROUND_US * per_us / (4.0 * (w - 1)))
+            raw_max_elems = max(1024, min(raw_max_elems, 1 << 20))
+        if oneshot_max_bytes is None:
+            # (W-1) - 2(W-1)/W bytes per element saved by two-shot vs ~1.5 flag rounds it adds
+            saved = (w - 1) - 2.0 * (w - 1) / w
+            oneshot_max_bytes = (1 << 40) if saved <= 0 else int(1.5 * self.FLAG_ROUND_US * per_us / saved)
+            oneshot_max_bytes = max(64 * 1024, min(oneshot_max_bytes, 8 << 20))
+        self.raw_max_elems, self.oneshot_max_bytes = int(raw_max_elems), int(oneshot_max_bytes)
+
+    def to_dict(self) -> dict:
+        return dict(world=self.world, link_gbs=self.link_gbs, multicast=self.multicast, raw_max_elems=self.raw_max_elems,
+                    oneshot_max_bytes=self.oneshot_max_bytes, source=self.source)
+
+
+_CALIBRATED = {}      # world size -> Thresholds installed by parallel.calibrate.calibrate()
+
+
+def default_thresholds(world: int) -> Thresholds:
+    if world in _CALIBRATED:
+        return _CALIBRATED[world]
+    link, mc = 900.0, True
+    try:
+        from .dist import discover_topology
+        topo = discover_topology()
+        link = topo.est_link_gbs or 900.0
+        mc = bool(topo.multicast)
+    except Exception:  # noqa: BLE001 - CPU-only box: constants are unused there
+        pass
+    return Thresholds(world, link, mc)
 
 
 class GradReducer:
@@ -63,7 +105,7 @@ class GradReducer:
     the reference algorithm on NCCL/Gloo (all_gather + one fold launch; fallback and oracle), "local" = world size 1.
     Buckets follow ``cfg.bucket_mb``; with ``cfg.overlap`` they launch from gradient hooks on a comm stream."""
     def __init__(self, arena: ModelArena, cfg: PrecisionConfig, group=None, mode: Optional[str] = None,
-                 timeout_cycles: int = 20_000_000_000):
+                 timeout_cycles: int = DEFAULT_TIMEOUT_CYCLES, thresholds: Optional[Thresholds] = None):
         self.arena = arena
         self.cfg = cfg
         self.group = group
@@ -73,6 +115,10 @@ class GradReducer:
         self.rank = dist.get_rank(group) if self.distributed else 0
         self.timeout_cycles = int(timeout_cycles)
         self.is_cuda = self.device.type == "cuda"
+        self.thresholds = thresholds or default_thresholds(self.world)
+        self.rounding = native.rounding_code(cfg.rounding)
+        # (8,23) without Kahan / APS is a plain sum: reference = NCCL all_reduce (dist_util.py:55-59)
+        self.plain_fp32 = cfg.is_fp32 and not cfg.use_kahan and not cfg.use_aps
 
         # wire width: narrow codes need already-quantised values (APS or prequantize)
         nat = native.wire_bits(cfg.grad_exp, cfg.grad_man)
@@ -95,7 +141,10 @@ class GradReducer:
                 mode = "fused"
         self.mode = mode
 
-        ranges = arena.bucket_ranges(cfg.bucket_mb * (1 << 20))
+        # overlap needs several buckets: default 8 MB of fp32 gradients each (a bucket's reduction then hides behind
+        # the backward of the layers below it); without overlap one launch covers the whole model
+        bucket_mb = cfg.bucket_mb if cfg.bucket_mb > 0 else (8.0 if cfg.overlap else 0.0)
+        ranges = arena.bucket_ranges(bucket_mb * (1 << 20))
         split = []
         for (a, b) in ranges:                      # the kernels keep per-tensor shifts in shared memory
             while b - a > MAX_TENSORS_PER_BUCKET:
@@ -114,7 +163,7 @@ class GradReducer:
             self.local_ws = torch.zeros(4 + 2 * MAX_TENSORS_PER_BUCKET + 32, dtype=torch.int32, device=self.device)
         if self.mode == "fused":
             from .symm import SymmetricWorkspace
-            cap = max(self.max_numel * (self.wire // 8), min(self.max_numel, RAW_MAX_ELEMS) * 4)
+            cap = max(self.max_numel * (self.wire // 8), min(self.max_numel, self.thresholds.raw_max_elems) * 4)
             if cfg.algo == "raw":
                 cap = self.max_numel * 4
             try:
@@ -130,9 +179,11 @@ class GradReducer:
         if self.mode == "gather" and self.world > 1:
             self._gather_buf = torch.empty(self.world, self.max_numel, dtype=torch.float32, device=self.device)
 
+        self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory() if self.is_cuda else None
         # overlap machinery
         self._hooks = []
         self._pending = None
+        self._last_ready_bucket = -1
         self._comm_stream = None
         self._launched = []
         if cfg.overlap and self.is_cuda and self.mode in ("fused", "gather", "local"):
@@ -146,12 +197,28 @@ class GradReducer:
         a = _ALGO.get(self.cfg.algo, native.ALGO_AUTO)
         if a != native.ALGO_AUTO:
             return a
+        th = self.thresholds
+        has_mc = self.symm is not None and self.symm.has_multicast
+        if self.plain_fp32:
+            if has_mc and b.numel * 4 > 64 * 1024:
+                return native.ALGO_NVLS_SUM                     # the switch does the sum (multimem.ld_reduce)
+            return native.ALGO_ONESHOT if (self.world <= 2 or b.numel * 4 <= th.oneshot_max_bytes) else native.ALGO_TWOSHOT
         nbytes = b.numel * (self.wire // 8)
-        if self.cfg.use_aps and b.numel <= RAW_MAX_ELEMS:
+        if self.cfg.use_aps and b.numel <= th.raw_max_elems:
             return native.ALGO_ONESHOT_RAW              # latency-bound: one flag round, raw fp32 on the wire
-        if self.world <= 2 or nbytes <= ONESHOT_MAX_BYTES:
+        if self.world <= 2 or nbytes <= th.oneshot_max_bytes:
             return native.ALGO_ONESHOT
-        return native.ALGO_NVLS if (self.symm is not None and self.symm.has_multicast) else native.ALGO_TWOSHOT
+        return native.ALGO_NVLS if has_mc else native.ALGO_TWOSHOT
+
+    def ctas_for(self, i: int) -> int:
+        """Grid of bucket ``i``'s launch.  Overlapped buckets co-run with backward kernels: a SMALL grid (cfg.comm_ctas,
+        default 32) leaves the SMs to them and stays co-resident (the kernel's grid barrier needs that); the bucket
+        that becomes ready LAST has nothing left to overlap with and takes the full grid."""
+        if self._pending is None:
+            return int(self.cfg.comm_ctas)
+        if i == self._last_ready_bucket:
+            return 0
+        return int(self.cfg.comm_ctas) or 32
 
     # ------------------------------------------------------------------- reduce --
     def reduce_bucket(self, i: int, grad_flat: Optional[torch.Tensor] = None) -> None:
@@ -165,12 +232,13 @@ class GradReducer:
             if cfg.is_fp32 and not cfg.use_kahan and not cfg.use_aps:
                 return                                           # fp32 all-reduce over one rank: nothing to do
             native.aps_fold([g], g, b.seg_off, e, m, cfg.use_aps, cfg.use_kahan, 1.0, chunks=b.chunks,
-                            workspace=self.local_ws, shifts_out=self.shifts[i], max_ctas=cfg.comm_ctas)
+                            workspace=self.local_ws, shifts_out=self.shifts[i], max_ctas=self.ctas_for(i),
+                            rounding=self.rounding)
         elif self.mode == "fused":
             native._C.allreduce_fused_cuda(
-                self.symm.buffers, g.data_ptr(), b.numel, b.chunks.data_ptr(), b.n_chunks, b.T, e, m,
-                bool(cfg.use_aps), bool(cfg.use_kahan), self.algo_for(b) | _PACK_HW, bool(cfg.prequantize), self.wire,
-                self.local_ws.data_ptr(), self.shifts[i].data_ptr(), int(cfg.comm_ctas), self.timeout_cycles,
+                self.symm.buffers, g.data_ptr(), b.numel, b.chunks.data_ptr(), b.n_chunks, b.T, e, m, self.rounding,
+                bool(cfg.use_aps), bool(cfg.use_kahan), self.algo_for(b) | _PROTO, bool(cfg.prequantize), self.wire,
+                self.local_ws.data_ptr(), self.shifts[i].data_ptr(), self.ctas_for(i), self.timeout_cycles,
                 torch.cuda.current_stream(self.device).cuda_stream)
         else:  # gather: the reference algorithm, one collective + one fold launch per bucket
             if cfg.is_fp32 and not cfg.use_kahan and not cfg.use_aps:
@@ -181,9 +249,10 @@ class GradReducer:
             srcs = [buf[r] for r in range(self.world)]
             if cfg.prequantize and not cfg.use_aps:
                 for s in srcs:
-                    native.quantize_(s, s, e, m)
+                    native.quantize_(s, s, e, m, cfg.rounding)
             native.aps_fold(srcs, g, b.seg_off, e, m, cfg.use_aps, cfg.use_kahan, float(self.world), chunks=b.chunks,
-                            workspace=self.local_ws, shifts_out=self.shifts[i], max_ctas=cfg.comm_ctas)
+                            workspace=self.local_ws, shifts_out=self.shifts[i], max_ctas=self.ctas_for(i),
+                            rounding=self.rounding)
 
     def reduce(self, grad_flat: Optional[torch.Tensor] = None) -> None:
         """Reduce every bucket now (call after backward)."""
@@ -202,6 +271,8 @@ class GradReducer:
                 owner[t] = bi
         self._bucket_need = [b.T for b in self.buckets]
         self._pending = [0] * len(self.buckets)
+        # gradients become ready from the last parameter to the first: the bucket holding tensor 0 fills last
+        self._last_ready_bucket = owner[0]
         self._armed = False
 
         def make_hook(bi):
@@ -247,13 +318,30 @@ class GradReducer:
 
     # ------------------------------------------------------------------- status --
     def check_status(self) -> None:
-        """Raise if a fused kernel timed out waiting for a peer (host-side sync point)."""
+        """Raise if a fused kernel timed out waiting for a peer (host-side sync point).  The kernel has then poisoned
+        the gradients it produced (NaN), so the step cannot have applied stale peer data silently."""
         if self.local_ws is None:
             return
-        st = int(self.local_ws[3].item()) & 0xFFFFFFFF
+        self._raise_on_status(int(self.local_ws[3].item()))
+
+    def status_async(self) -> Optional[torch.Tensor]:
+        """Start a 4-byte device->pinned-host copy of the status word on the current stream (the training engine issues
+        it next to the loss read-back of every step and calls ``check_status_host`` after its event sync)."""
+        if self.local_ws is None or self.mode != "fused":
+            return None
+        self._status_host.copy_(self.local_ws[3:4], non_blocking=True)
+        return self._status_host
+
+    def check_status_host(self) -> None:
+        if self._status_host is not None and self.mode == "fused":
+            self._raise_on_status(int(self._status_host[0]))
+
+    def _raise_on_status(self, st: int) -> None:
+        st &= 0xFFFFFFFF
         if st & 0x80000000:
             phase, peer = (st >> 8) & 0xFF, st & 0xFF
-            raise RuntimeError(f"cpd_b200: fused all-reduce timed out in phase {phase} waiting for rank {peer}")
+            raise RuntimeError(f"cpd_b200: fused all-reduce timed out in phase {phase} waiting for rank {peer} "
+                               f"(rank {self.rank} poisoned its gradients with NaN)")
 
     def phase_times_us(self) -> dict:
         """Per-phase durations (us) of the LAST fused launch, from the %globaltimer stamps CTA 0 leaves in the

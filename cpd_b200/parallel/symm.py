@@ -77,7 +77,8 @@ class SymmetricWorkspace:
             self.rank, self.world,
             [p + self.off_data for p in ptrs], [p + self.off_gather for p in ptrs],
             [p + self.off_mailbox for p in ptrs], [p + self.off_flags for p in ptrs],
-            (self.mc_base + self.off_gather) if self.mc_base else 0, self.cap_bytes, self.max_tensors)
+            (self.mc_base + self.off_gather) if self.mc_base else 0, self.cap_bytes, self.max_tensors,
+            (self.mc_base + self.off_data) if self.mc_base else 0)
         torch.cuda.synchronize()
         dist.barrier(group=group)
 

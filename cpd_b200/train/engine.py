@@ -184,8 +184,10 @@ class TrainEngine:
         """Device -> host read of the step's (local, already /W) loss."""
         if self.is_cuda:
             self.loss_host.copy_(self.loss_dev, non_blocking=True)
+            self.reducer.status_async()                    # 4 more bytes next to the loss: a timed-out peer raises NOW
             self._done_evt.record()
             self._done_evt.synchronize()
+            self.reducer.check_status_host()
         else:
             self.loss_host.copy_(self.loss_dev)
         return float(self.loss_host[0])
@@ -226,8 +228,10 @@ class TrainEngine:
         self.run_step()
         if self.is_cuda:
             self.loss_host.copy_(self.loss_dev, non_blocking=True)
+            self.reducer.status_async()                    # 4 more bytes next to the loss: a timed-out peer raises NOW
             self._done_evt.record()
             self._done_evt.synchronize()
+            self.reducer.check_status_host()
         else:
             self.loss_host.copy_(self.loss_dev)
         return float(self.loss_host[0])
@@ -283,5 +287,7 @@ class TrainEngine:
             cur = self.model.state_dict()
             for k, v in sd["model"].items():
                 cur[k].copy_(v)
-        self.optimizer.load_state_dict(sd["optimizer"])
+        self.optimizer.resync_master()
+        if sd.get("optimizer") is not None:
+            self.optimizer.load_state_dict(sd["optimizer"])
         self.step_count = int(sd.get("step", 0))

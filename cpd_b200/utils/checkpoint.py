@@ -67,8 +67,13 @@ def load_state(path: str, model, optimizer=None, strict: bool = False, map_locat
                 cur[k].copy_(v)            # copy into the existing (arena-backed) storage
         if strict and missing:
             raise KeyError(f"missing keys in checkpoint: {missing[:5]}...")
-    if optimizer is not None and "optimizer" in ckpt:
-        optimizer.load_state_dict(ckpt["optimizer"])
+    if optimizer is not None:
+        # FusedSGD keeps fp32 masters that the step copies back into the model: re-derive them from the weights just
+        # loaded, THEN let a compatible optimizer state (ours, or a torch.optim.SGD dict as the reference saves) refine
+        if hasattr(optimizer, "resync_master"):
+            optimizer.resync_master()
+        if "optimizer" in ckpt:
+            optimizer.load_state_dict(ckpt["optimizer"])
     if "rng" in ckpt and ckpt["rng"].get("torch") is not None:
         torch.set_rng_state(ckpt["rng"]["torch"])
     return float(ckpt.get("best_prec1", 0.0)), int(ckpt.get("step", ckpt.get("epoch", 0)))

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--bf16", action="store_true", help="bf16 forward/backward (autocast)")
     ap.add_argument("--data", default="")
     ap.add_argument("--dataset_len", default=50000, type=int)
+    ap.add_argument("--cpu", action="store_true", help="run on the CPU backend (C++ CPU ops, Gloo)")
     add_precision_args(ap, grad_exp=8, grad_man=23)
     args = ap.parse_args()
     rank, world = dist_init() if (args.dist == 1 and "RANK" in os.environ or "SLURM_PROCID" in os.environ) else (0, 1)
@@ -47,7 +48,8 @@ def main():
     B = args.batch_size
     engine = TrainEngine(create_model("davidnet"), cfg, batch_size=B, lr=0.0, momentum=args.momentum, weight_decay=5e-4 * B,
                          nesterov=not args.use_lars, use_lars=args.use_lars, loss_reduction="sum", loss_scale=args.loss_scale,
-                         amp_dtype=torch.bfloat16 if args.bf16 else (torch.float16 if args.half else None))
+                         amp_dtype=torch.bfloat16 if args.bf16 else (torch.float16 if args.half else None),
+                         device=torch.device("cpu") if args.cpu else None)
     if args.data:
         import torchvision
         raw = torchvision.datasets.CIFAR10(args.data, train=True)

@@ -33,15 +33,23 @@ def main():
     ap.add_argument("-e", "--evaluate", action="store_true")
     ap.add_argument("--data", default="", help="CIFAR-10 root (torchvision layout); synthetic data of the same shape if empty")
     ap.add_argument("--max-iter", dest="max_iter_override", type=int, default=0)
+    # command-line overrides of the YAML's `common:` keys (the reference can only edit the file, mix.py:69-72)
+    for key, typ in (("arch", str), ("batch_size", int), ("workers", int), ("dataset_len", int), ("val_freq", int),
+                     ("print_freq", int), ("save_path", str), ("max_epoch", int)):
+        ap.add_argument("--" + key, "--" + key.replace("_", "-"), dest="cli_" + key, type=typ, default=None)
+    ap.add_argument("--val-len", dest="val_len", type=int, default=2048)
+    ap.add_argument("--cpu", action="store_true", help="run on the CPU backend (C++ CPU ops, Gloo)")
     add_precision_args(ap, grad_exp=5, grad_man=2)
     args = ap.parse_args()
     with open(args.config) as f:
         for k, v in yaml.safe_load(f)["common"].items():
-            setattr(args, k, v)
+            cli = getattr(args, "cli_" + k, None)
+            setattr(args, k, v if cli is None else cli)
     rank, world = dist_init() if args.dist else (0, 1)
     cfg = PrecisionConfig.from_args(args)
     engine = TrainEngine(create_model(args.arch), cfg, batch_size=args.batch_size, lr=args.base_lr, momentum=args.momentum,
-                         weight_decay=args.weight_decay, use_lars=args.use_lars)
+                         weight_decay=args.weight_decay, use_lars=args.use_lars,
+                         device=torch.device("cpu") if args.cpu else None)
     if args.data:
         import torchvision
         import torchvision.transforms as T
@@ -50,7 +58,7 @@ def main():
             [T.RandomCrop(32, padding=4), T.RandomHorizontalFlip(), T.ToTensor(), norm]))
         val_ds = torchvision.datasets.CIFAR10(args.data, train=False, transform=T.Compose([T.ToTensor(), norm]))
     else:
-        train_ds, val_ds = cifar_shape(args.dataset_len), cifar_shape(2048, seed=1)
+        train_ds, val_ds = cifar_shape(args.dataset_len), cifar_shape(args.val_len, seed=1)
     E = cfg.emulate_node
     it_per_epoch = len(train_ds) / (world * args.batch_size * E)
     max_iter = args.max_iter_override or math.ceil(it_per_epoch * args.max_epoch)                  # mix.py:131-132

@@ -40,13 +40,16 @@ def main():
     ap.add_argument("--data", default="", help="ImageFolder root with train/ and val/; synthetic if empty")
     ap.add_argument("--dataset-len", type=int, default=4096)
     ap.add_argument("--max-iter", type=int, default=0)
+    ap.add_argument("--val-len", type=int, default=256)
+    ap.add_argument("--workers", type=int, default=4)
+    ap.add_argument("--arch", default="resnet50")
     add_precision_args(ap, grad_exp=5, grad_man=2)
     args = ap.parse_args()
     rank, world = dist_init() if ("RANK" in os.environ or "SLURM_PROCID" in os.environ) else (0, 1)
     torch.manual_seed(args.seed)
     torch.backends.cudnn.benchmark = True
     cfg = PrecisionConfig.from_args(args)
-    model = create_model("resnet50")
+    model = create_model(args.arch)
     engine = TrainEngine(model, cfg, batch_size=args.batch_size, input_shape=(3, 224, 224), lr=args.base_lr, momentum=args.momentum,
                          weight_decay=args.wd, nesterov=True, wd_mult=bn_bias_no_decay(model.named_parameters()), fold_single=True,
                          device=torch.device("cpu") if args.no_cuda else None)
@@ -57,7 +60,7 @@ def main():
         train_ds = D.ImageFolder(os.path.join(args.data, "train"), T.Compose([T.RandomResizedCrop(224), T.RandomHorizontalFlip(), T.ToTensor(), norm]))
         val_ds = D.ImageFolder(os.path.join(args.data, "val"), T.Compose([T.Resize(256), T.CenterCrop(224), T.ToTensor(), norm]))
     else:
-        train_ds, val_ds = imagenet_shape(args.dataset_len), imagenet_shape(256, seed=1)
+        train_ds, val_ds = imagenet_shape(args.dataset_len), imagenet_shape(args.val_len, seed=1)
     E = cfg.emulate_node
     it_per_epoch = len(train_ds) // (world * args.batch_size * E)
     peak = args.base_lr * world * E * (args.batch_size / 32.0) * 32        # main.py: lr scales with the global batch (3.2 at 8 x 32)
@@ -67,7 +70,7 @@ def main():
     def batches():
         for epoch in range(args.epochs):
             sampler.set_epoch(epoch)
-            yield from torch.utils.data.DataLoader(train_ds, batch_size=args.batch_size * E, sampler=sampler, num_workers=4,
+            yield from torch.utils.data.DataLoader(train_ds, batch_size=args.batch_size * E, sampler=sampler, num_workers=args.workers,
                                                    pin_memory=True, drop_last=True)
 
     def val_batches():

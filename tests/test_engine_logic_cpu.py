@@ -66,19 +66,28 @@ def test_reducer_wire_and_mode_selection():
 
 
 def test_variant_selection_follows_the_measured_thresholds():
-    """algo_for(): raw (one flag round) for tiny APS buckets, packed one-shot up to ONESHOT_MAX_BYTES of wire codes,
-    NVLS / two-shot above; 2 ranks always one-shot; a forced algo is honoured."""
+    """algo_for(): raw (one flag round) for small APS buckets, packed one-shot up to the one-shot limit of wire codes,
+    NVLS / two-shot above; plain fp32 -> in-switch sum; 2 ranks always one-shot; a forced algo is honoured.  The limits
+    come from the topology (link bandwidth x flag-round latency) or from a calibration run."""
     from types import SimpleNamespace
     from cpd_b200.ops import native
     from cpd_b200.parallel import reducer as R
+    th8 = R.Thresholds(8, link_gbs=900.0)
+    assert 200_000 < th8.raw_max_elems < 300_000 and 1 << 20 <= th8.oneshot_max_bytes <= 4 << 20
+    assert R.Thresholds(2, link_gbs=900.0).raw_max_elems > th8.raw_max_elems        # fewer peers: raw pays longer
+    assert R.Thresholds(8, link_gbs=450.0).raw_max_elems < th8.raw_max_elems        # slower links: hand over earlier
     arena = ModelArena(list(_net().parameters()))
     r = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True))
     bucket = lambda n: SimpleNamespace(numel=n)                                     # noqa: E731
     r.world, r.symm = 8, SimpleNamespace(has_multicast=True)
-    assert r.algo_for(bucket(R.RAW_MAX_ELEMS)) == native.ALGO_ONESHOT_RAW
-    assert r.algo_for(bucket(R.RAW_MAX_ELEMS + 16)) == native.ALGO_ONESHOT
-    assert r.algo_for(bucket(R.ONESHOT_MAX_BYTES)) == native.ALGO_ONESHOT            # 8-bit wire: bytes == elements
-    assert r.algo_for(bucket(R.ONESHOT_MAX_BYTES + 16)) == native.ALGO_NVLS
+    r.thresholds = th = R.Thresholds(8, raw_max_elems=4096, oneshot_max_bytes=1 << 19, source="test")
+    assert r.algo_for(bucket(th.raw_max_elems)) == native.ALGO_ONESHOT_RAW
+    assert r.algo_for(bucket(th.raw_max_elems + 16)) == native.ALGO_ONESHOT
+    assert r.algo_for(bucket(th.oneshot_max_bytes)) == native.ALGO_ONESHOT            # 8-bit wire: bytes == elements
+    assert r.algo_for(bucket(th.oneshot_max_bytes + 16)) == native.ALGO_NVLS
+    r.plain_fp32 = True
+    assert r.algo_for(bucket(1 << 20)) == native.ALGO_NVLS_SUM
+    r.plain_fp32 = False
     r.symm = SimpleNamespace(has_multicast=False)
     assert r.algo_for(bucket(1 << 24)) == native.ALGO_TWOSHOT
     r.world = 2

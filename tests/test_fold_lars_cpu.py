@@ -71,6 +71,29 @@ def test_aps_prevents_underflow_that_plain_low_precision_suffers():
     assert err_aps < 0.15 and err_plain > 0.5
 
 
+def test_rounding_mode_reaches_the_gradient_fold():
+    """PrecisionConfig.rounding must act on the gradient path.  Quirk B (truncating subnormal shift) makes the
+    reference cast of 0.5*ulp_min*(1+2^-20) zero where IEEE rounds up; the fold of one source shows which cast ran."""
+    from cpd_b200 import PrecisionConfig, float_quantize
+    from cpd_b200.parallel import GradReducer, ModelArena
+    layout = ArenaLayout([64])
+    ulp_min = 2.0 ** (1 - 7 - 3)                          # (4,3): smallest subnormal
+    x = torch.full((layout.total,), 0.5 * ulp_min * (1 + 2.0 ** -20))
+    tab = layout.table("cpu")
+    ref, ieee = torch.empty(layout.total), torch.empty(layout.total)
+    native.aps_fold([x], ref, tab.seg_off, 4, 3, False, False, 1.0, rounding="reference")
+    native.aps_fold([x], ieee, tab.seg_off, 4, 3, False, False, 1.0, rounding="ieee")
+    assert torch.equal(ref, float_quantize(x, 4, 3, "reference")) and float(ref[0]) == 0.0
+    assert torch.equal(ieee, float_quantize(x, 4, 3, "ieee")) and float(ieee[0]) == ulp_min
+    # ... and through the public reducer (world size 1, no APS so the raw value reaches the cast)
+    lin = torch.nn.Linear(8, 8, bias=False)
+    arena = ModelArena(list(lin.parameters()))
+    for name, want in (("reference", 0.0), ("ieee", ulp_min)):
+        arena.grad_flat.fill_(float(x[0]))
+        GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, rounding=name)).reduce()
+        assert float(arena.grad_flat[0]) == want, name
+
+
 def test_fp32_identity_is_plain_sum():
     layout = ArenaLayout([1000])
     g = [torch.randn(layout.total) for _ in range(4)]

@@ -102,6 +102,43 @@ def test_checkpoint_save_resume_reproduces_next_step(tmp_path):
     assert load_state(str(tmp_path / "m.pth"), b.model)[1] == 9
 
 
+def test_model_only_and_foreign_optimizer_checkpoints_survive_a_step(tmp_path):
+    """a checkpoint without a cpd optimizer entry must not be reverted by the next step (the step copies
+    the fp32 masters into the model), and a reference-format torch.optim.SGD state_dict must load, not KeyError."""
+    from cpd_b200.train import TrainEngine
+    def make():
+        torch.manual_seed(0)
+        m = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(48, 16), torch.nn.ReLU(), torch.nn.Linear(16, 10))
+        return TrainEngine(m, PrecisionConfig(grad_exp=8, grad_man=23), batch_size=4, input_shape=(3, 4, 4), lr=0.0,
+                           weight_decay=0.0, use_lars=False, cuda_graph=False)
+    x, y = torch.randn(4, 3, 4, 4), torch.randint(0, 10, (4,))
+    eng = make()
+    sd = {"state_dict": {k: torch.full_like(v, 0.5) for k, v in eng.model.state_dict().items()}, "step": 1}
+    torch.save(sd, str(tmp_path / "model_only.pth"))
+    load_state(str(tmp_path / "model_only.pth"), eng.model, eng.optimizer)
+    eng.train_step(x, y)                                   # lr = 0: the weights must stay what was loaded
+    assert all(bool((p == 0.5).all()) for p in eng.model.parameters())
+    # reference-style checkpoint: torch SGD state_dict under 'optimizer' (mix.py:345-356)
+    ref_model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(48, 16), torch.nn.ReLU(), torch.nn.Linear(16, 10))
+    opt = torch.optim.SGD(ref_model.parameters(), lr=0.3, momentum=0.9)
+    ref_model(x).sum().backward()
+    opt.step()
+    torch.save({"state_dict": ref_model.state_dict(), "optimizer": opt.state_dict(), "step": 2}, str(tmp_path / "ref.pth"))
+    eng2 = make()
+    _, last = load_state(str(tmp_path / "ref.pth"), eng2.model, eng2.optimizer)
+    assert last == 2 and eng2.optimizer.lr == pytest.approx(0.3)
+    for p, q in zip(eng2.model.parameters(), ref_model.parameters()):
+        assert torch.equal(p.detach(), q.detach())
+    moms = [eng2.arena.layout.view(eng2.optimizer.mom, t, like=p.data) for t, p in enumerate(eng2.arena.params)]
+    for mview, q in zip(moms, ref_model.parameters()):
+        assert torch.equal(mview, opt.state[q]["momentum_buffer"])
+    eng2.set_lr(0.0)
+    eng2.optimizer.momentum = 0.0
+    eng2.train_step(x, y)
+    for p, q in zip(eng2.model.parameters(), ref_model.parameters()):
+        assert torch.equal(p.detach(), q.detach())
+
+
 def test_config_flags_accept_both_spellings():
     p = argparse.ArgumentParser()
     add_precision_args(p)

@@ -31,6 +31,27 @@ def test_fused_allreduce_fake_world_matches_cpu_fold(world):
     assert "mismatching cases: none" in r.stdout, r.stdout[-3000:]
 
 
+@pytest.mark.timeout(200)
+def test_fused_allreduce_timeout_poisons_outputs_and_names_the_missing_rank():
+    """SURVEY §5.3 fault injection: a peer that never signals must not hang the kernel NOR leak stale data into the
+    gradients — bounded spin, NaN-poisoned outputs, status word -> RuntimeError naming rank and phase (tools/fault_timeout.py)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29650 + os.getpid() % 200))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fault_timeout.py")], capture_output=True, text=True,
+                       timeout=180, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("FAULT_TIMEOUT ")][-1]
+    res = json.loads(line[len("FAULT_TIMEOUT "):])
+    assert [x["algo"] for x in res] == ["raw", "oneshot", "twoshot"]
+    for x in res:
+        assert x["returned_ms"] < 1000, x                      # bounded: a few timeouts of ~2 ms, not a hang
+        assert x["all_nan"], x
+        assert "timed out" in x["error"] and "waiting for rank 1" in x["error"], x
+
+
 @pytest.mark.parametrize("e,m", [(4, 3), (5, 2), (5, 10), (6, 9)])
 @pytest.mark.parametrize("aps,kahan", [(True, False), (True, True), (False, False), (False, True)])
 def test_aps_fold_32_sources_matches_cpu(e, m, aps, kahan):
@@ -66,8 +87,12 @@ def test_quantize_more_than_2_31_elements():
     float_quantize(x, 4, 3, inplace=True)
     assert _same(x[-4099:], float_quantize(tail, 4, 3))
     assert _same(x[:1024], float_quantize(torch.full((1024,), 1.2345), 4, 3))
-    mid = (1 << 31) - 512
+    # the 1024 elements that end exactly at the 2^31 boundary (the linspace tail starts there)
+    mid = (1 << 31) - 1024
     assert _same(x[mid:mid + 1024], float_quantize(torch.full((1024,), 1.2345), 4, 3))
+    # ... and a window that straddles 2^31: constant part | first 512 elements of the tail
+    assert _same(x[(1 << 31) - 512:(1 << 31) + 512],
+                 float_quantize(torch.cat([torch.full((512,), 1.2345), tail[:512]]), 4, 3))
     del x
     torch.cuda.empty_cache()
 

@@ -214,6 +214,44 @@ def section_stress(rank, world, res, iters):
     res["stress_all_pass"] = all(v["mismatching_checks"] == 0 for v in out.values())
 
 
+def section_fault(rank, world, res):
+    """rank `world - 1` reaches the collective late (torch.cuda._sleep, the same hook as
+    CPD_B200_FAULT_DELAY_RANK); with a short timeout every OTHER rank must return (no hang), poison its gradients and
+    raise a RuntimeError that names the late rank."""
+    from cpd_b200.parallel import reducer as R
+    dev = torch.device("cuda", torch.cuda.current_device())
+    late = world - 1
+    out = {}
+    for algo in ("oneshot", "twoshot"):
+        arena = FakeArena([4096, 300, 70000], dev)
+        fill(arena, rank, seed=11)
+        red = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, algo=algo), mode="fused",
+                          timeout_cycles=20_000_000)                               # ~10 ms
+        red.reduce()                                                                # a healthy launch first
+        torch.cuda.synchronize()
+        red.check_status()
+        dist.barrier()
+        old = (R._FAULT_DELAY_RANK, R._FAULT_DELAY_CYCLES)
+        R._FAULT_DELAY_RANK, R._FAULT_DELAY_CYCLES = late, 4e8                      # ~200 ms >> timeout
+        fill(arena, rank, seed=12)
+        red.reduce()
+        torch.cuda.synchronize()
+        R._FAULT_DELAY_RANK, R._FAULT_DELAY_CYCLES = old
+        msg = ""
+        try:
+            red.check_status()
+        except RuntimeError as e:
+            msg = str(e)
+        ok = (rank == late) or (f"waiting for rank {late}" in msg and bool(torch.isnan(arena.grad_flat[:4096]).all()))
+        t = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        out[algo] = dict(all_on_time_ranks_raised_and_poisoned=bool(t.item()), rank0_error=msg if rank == 0 else None)
+        del red
+        dist.barrier()
+    res["fault"] = out
+    res["fault_all_pass"] = all(v["all_on_time_ranks_raised_and_poisoned"] for v in out.values())
+
+
 def reference_algorithm(g, world, e, m, gather_buf):
     """dist_util.py:54-69 with our quantize kernel: all_gather fp32 + W x {add, quantize}."""
     bufs = [gather_buf[r] for r in range(world)]
@@ -358,6 +396,10 @@ def main():
                 print("[stress]", json.dumps(res["stress"]), flush=True)
         if "sweep" in secs:
             section_sweep(rank, world, res, args.max_bytes)
+        if "fault" in secs:                       # last: the timed-out reducers leave their status words set
+            section_fault(rank, world, res)
+            if rank == 0:
+                print("[fault]", json.dumps(res["fault"]), flush=True)
     except Exception:  # noqa: BLE001
         res["error"] = traceback.format_exc()
         print(f"[rank {rank}] ERROR\n{res['error']}", flush=True)
@@ -365,7 +407,7 @@ def main():
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
         with open(args.out, "w") as f:
             json.dump(res, f, indent=1)
-    ok = res.get("correct_all_pass", True) and res.get("stress_all_pass", True) and "error" not in res
+    ok = res.get("correct_all_pass", True) and res.get("stress_all_pass", True) and res.get("fault_all_pass", True) and "error" not in res
     try:
         dist.barrier()
         dist.destroy_process_group()
