@@ -52,7 +52,7 @@ class RefRunner:
     """One model + the reference's training step."""
 
     def __init__(self, model_name: str, batch: int, grad_exp: int, grad_man: int, use_aps: bool, use_kahan: bool,
-                 use_lars: bool):
+                 use_lars: bool, gemm_exp: int = 5, gemm_man: int = 10):
         import torch
         import torch.nn as nn
         from CPDtorch.utils.dist_util import dist_init, sum_gradients, DistModule
@@ -64,10 +64,27 @@ class RefRunner:
         self.grad_exp, self.grad_man, self.use_aps, self.use_kahan, self.use_lars = grad_exp, grad_man, use_aps, use_kahan, use_lars
         import torch.distributed as dist
         self.dist = dist
-        if model_name == "resnet18":
+        if model_name in ("resnet18", "resnet18_quant"):
             sys.path.insert(0, os.path.join(REF, "example", "ResNet18"))
             import models as ref_models                                        # example/ResNet18/models
             self.model = ref_models.__dict__["res_cifar"]()                      # mix.py:81 (arch: res_cifar)
+            if model_name == "resnet18_quant":
+                # the reference ships Quant_Conv as a library module (CPDtorch/quant/quant_module.py:88-139) and no model
+                # that uses it: swap it in for every nn.Conv2d of the reference's own ResNet-18 (README.md:9 "customized-
+                # precision floating point as accumulator while GEMM"); F.unfold + tvm_gemm underneath, (gemm_exp, gemm_man).
+                # The 10-class head stays nn.Linear: tvm_gemm's M-remainder branch (rows beyond the last multiple of 16)
+                # reads an uninitialised accumulator (float_kernel.cu:221-339).
+                from CPDtorch.quant import Quant_Conv as RefQuantConv
+
+                def swap(mod):
+                    for name, child in list(mod.named_children()):
+                        if isinstance(child, nn.Conv2d):
+                            q = RefQuantConv(child.in_channels, child.out_channels, child.kernel_size[0], stride=child.stride[0],
+                                             padding=child.padding[0], bias=child.bias is not None, exp=gemm_exp, man=gemm_man)
+                            setattr(mod, name, q)
+                        else:
+                            swap(child)
+                swap(self.model)
             self.model.cuda()
             for p in self.model.parameters():                                  # mix.py:86-88
                 dist.broadcast(p, 0)
@@ -116,7 +133,7 @@ class RefRunner:
     def step(self) -> float:
         x, y = self.pool[self.i % len(self.pool)]
         self.i += 1
-        return getattr(self, "_step_" + self.model_name)(x, y)
+        return getattr(self, "_step_" + self.model_name.replace("_quant", ""))(x, y)
 
     def _step_resnet18(self, input, target) -> float:
         torch, dist = self.torch, self.dist

@@ -34,6 +34,12 @@ CONFIGS = {
                      use_kahan=False, use_lars=False, nesterov=True, lr=0.1, wd=1e-4, loss="mean", label="ResNet-50/ImageNet-shape"),
     "davidnet": dict(arch="davidnet", batch=512, shape=(3, 32, 32), classes=10, grad_exp=5, grad_man=2, use_aps=True,
                      use_kahan=True, use_lars=True, nesterov=False, lr=0.1, wd=5e-4, loss="mean", label="DavidNet/CIFAR-shape"),
+    # the custom-precision GEMM on a hot path: every convolution of ResNet-18 is a Quant_Conv with an fp16-shaped (5,10)
+    # accumulator (reference: its own Quant_Conv = F.unfold + tvm_gemm; ours: tcgen05 tile mode, bf16 operands, fused
+    # im2col/cast staging).  Per-GPU batch 64: the reference's SIMT GEMM needs ~1 s per step already.
+    "resnet18_quant": dict(arch="resnet18_cifar_quant", batch=64, shape=(3, 32, 32), classes=10, grad_exp=4, grad_man=3, use_aps=True,
+                           use_kahan=False, use_lars=False, nesterov=False, lr=0.1, wd=1e-4, loss="mean",
+                           gemm_exp=5, gemm_man=10, label="ResNet-18/CIFAR-shape with Quant_Conv (5,10) GEMM accumulators"),
 }
 # published reference numbers: only ResNet-50 has one (<= ~1068 img/s on 8xV100, derived bound)
 PUBLISHED = {"resnet50": 1068.0}
@@ -78,6 +84,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(rows)}
 
 
+def shared_config(model_key: str, cfg: dict, world: int, emulate_node: int = 1) -> dict:
+    """The part of `config` that names the benchmark: IDENTICAL keys and values in both arms (the driver compares them)."""
+    out = {"model": cfg["arch"], "global_batch": cfg["batch"] * emulate_node * world, "per_gpu_batch": cfg["batch"],
+           "image_shape": list(cfg["shape"]), "parallelism": f"dp{world}", "grad_format": f"exp{cfg['grad_exp']}man{cfg['grad_man']}",
+           "use_APS": cfg["use_aps"], "use_kahan": cfg["use_kahan"], "use_lars": cfg["use_lars"], "emulate_node": emulate_node,
+           "optimizer": "LARS" if cfg["use_lars"] else "SGD",
+           "l2": "per-step working set (activations + gradients) exceeds the 126 MB L2; no explicit flush"}
+    if "gemm_exp" in cfg:
+        out["gemm_accumulator_format"] = f"exp{cfg['gemm_exp']}man{cfg['gemm_man']}"
+    return out
+
+
+METRIC = "{label} training images/sec (device-timed, max over ranks)"
+DTYPE = "fp32 (cuDNN TF32 convolutions, torch defaults — the reference's stock fp32 path on both arms)"
+DATA = "synthetic (random-init weights, random images/labels of the named shape)"
+
+
 def timed(fn_step, steps: int, torch, dist, world: int):
     """barrier + sync | CUDA events around exactly `steps` calls | sync; max over ranks (ms)."""
     if world > 1:
@@ -120,7 +143,8 @@ def run_ours(args, cfg):
     torch.manual_seed(0)
     pc = PrecisionConfig(grad_exp=cfg["grad_exp"], grad_man=cfg["grad_man"], use_aps=cfg["use_aps"], use_kahan=cfg["use_kahan"],
                          algo=args.algo, overlap=args.overlap, bucket_mb=args.bucket_mb, emulate_node=args.emulate_node)
-    model = create_model(cfg["arch"])
+    model_kw = dict(exp=cfg["gemm_exp"], man=cfg["gemm_man"], mode="tile", operands="bf16") if "gemm_exp" in cfg else {}
+    model = create_model(cfg["arch"], **model_kw)
     wd_mult = bn_bias_no_decay(model.named_parameters()) if args.model == "resnet50" else None
     eng = TrainEngine(model, pc, batch_size=cfg["batch"], input_shape=cfg["shape"], lr=cfg["lr"], momentum=0.9,
                       weight_decay=cfg["wd"], use_lars=cfg["use_lars"], nesterov=cfg["nesterov"], wd_mult=wd_mult,
@@ -162,33 +186,30 @@ def run_ours(args, cfg):
     imgs = cfg["batch"] * pc.emulate_node * world * args.steps
     value = imgs / (ms_dev / 1e3)
     e2e = imgs / (ms_e2e / 1e3)
-    launches_per_step = (1 if eng.emulate.active else 0) + len(eng.reducer.buckets) + 1
-    if eng.reducer.mode == "local" and pc.is_fp32 and not pc.use_aps and not pc.use_kahan:
-        launches_per_step -= len(eng.reducer.buckets)
+    # counted by the native library while ONE step was issued (every launcher bumps an atomic); the captured CUDA graph
+    # replays exactly these kernels every step, and the e2e loop runs the same graph
+    launches_per_step = int(eng.kernel_launches_per_step or 0)
     if rank == 0:
+        config = shared_config(args.model, cfg, world, pc.emulate_node)
         out = {
-            "metric": f"{cfg['label']} training images/sec (device-timed, max over ranks)", "value": round(value, 1),
+            "metric": METRIC.format(label=cfg["label"]), "value": round(value, 1),
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "warmup_untimed_steps_run": max(args.warmup, 3) + 3,      # W (>= 3) + 3 more so the CUDA-graph capture is never timed
             "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": (round(value / PUBLISHED[args.model], 3) if args.model in PUBLISHED else None),
-            "dtype": "fp32 (cuDNN TF32 convolutions, torch defaults — same as the reference's stock fp32 path)",
-            "data": "synthetic (random-init weights, random images/labels of the named shape)",
-            "impl": "ours",
-            "config": {"model": cfg["arch"], "global_batch": cfg["batch"] * pc.emulate_node * world, "per_gpu_batch": cfg["batch"],
-                       "image_shape": list(cfg["shape"]), "parallelism": f"dp{world}",
-                       "grad_format": f"exp{pc.grad_exp}man{pc.grad_man}", "use_APS": pc.use_aps, "use_kahan": pc.use_kahan,
-                       "use_lars": cfg["use_lars"], "emulate_node": pc.emulate_node, "optimizer": "LARS" if cfg["use_lars"] else "SGD",
-                       "allreduce": eng.reducer.mode + (":" + (eng.reducer.symm.backend if eng.reducer.symm else "-")),
-                       "nvls": bool(eng.reducer.symm.has_multicast) if eng.reducer.symm else False,
-                       "wire_bits": eng.reducer.wire, "buckets": len(eng.reducer.buckets), "cuda_graph": not args.no_graph,
-                       "channels_last": not args.nchw, "e2e_input_pipelining": bool(args.pipelined),
-                       "l2": "per-step working set (activations+gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush"},
+            "dtype": DTYPE, "data": DATA, "impl": "ours", "config": config,
+            "impl_detail": {"allreduce": eng.reducer.mode + (":" + (eng.reducer.symm.backend if eng.reducer.symm else "-")),
+                            "nvls": bool(eng.reducer.symm.has_multicast) if eng.reducer.symm else False,
+                            "wire_bits": eng.reducer.wire, "buckets": len(eng.reducer.buckets), "overlap": bool(pc.overlap),
+                            "thresholds": eng.reducer.thresholds.to_dict(), "cuda_graph": not args.no_graph,
+                            "channels_last": not args.nchw, "e2e_input_pipelining": bool(args.pipelined)},
             "e2e": {"value": round(e2e, 1), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 3),
-                    "h2d_bytes_per_step": stream.bytes_per_batch, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": stream.bytes_per_batch, "d2h_bytes_per_step": 8,
+                    "note": "TrainEngine.train_step" + ("_pipelined" if args.pipelined else "") +
+                            ": pinned H2D of the batch + D2H of the loss and of the all-reduce status word, every step"},
             "gpu_launches": launches_per_step * args.steps,
-            "gpu_launches_note": f"{launches_per_step} cpd_b200 kernels per step (emulate fold / fused all-reduce per bucket / fused optimizer), "
-                                 "inside a captured CUDA graph with the cuDNN forward/backward",
+            "gpu_launches_note": f"{launches_per_step} cpd_b200 kernel launches per step, counted by the native library "
+                                 "(cpd_b200._C.launch_count) while the step was captured; the CUDA graph replays them every step",
             "clocks": clocks, "final_loss": round(losses[-1], 4),
         }
         print(json.dumps(out), flush=True)
@@ -212,7 +233,7 @@ def run_reference(args, cfg):
         import torch
         import torch.distributed as dist
         runner = ref_harness.RefRunner(args.model, cfg["batch"], cfg["grad_exp"], cfg["grad_man"], cfg["use_aps"],
-                                       cfg["use_kahan"], cfg["use_lars"])
+                                       cfg["use_kahan"], cfg["use_lars"], gemm_exp=cfg.get("gemm_exp", 5), gemm_man=cfg.get("gemm_man", 10))
     except Exception as e:  # noqa: BLE001
         if rank == 0:
             print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {str(e)[:300]}"}))
@@ -230,16 +251,16 @@ def run_reference(args, cfg):
     value = imgs / (ms / 1e3)
     if rank == 0:
         out = {
-            "metric": f"{cfg['label']} training images/sec (device-timed, max over ranks)", "value": round(value, 1),
+            "metric": METRIC.format(label=cfg["label"]), "value": round(value, 1),
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "warmup_untimed_steps_run": max(args.warmup, 3),
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": (round(value / PUBLISHED[args.model], 3) if args.model in PUBLISHED else None),
-            "dtype": "fp32 (cuDNN TF32 convolutions, torch defaults)", "data": "synthetic", "impl": "reference",
-            "config": {"model": args.model, "global_batch": cfg["batch"] * world, "per_gpu_batch": cfg["batch"], "parallelism": f"dp{world}",
-                       "grad_format": f"exp{cfg['grad_exp']}man{cfg['grad_man']}", "use_APS": cfg["use_aps"], "use_kahan": cfg["use_kahan"],
-                       "use_lars": cfg["use_lars"], "path": "unmodified drcut/CPD from baseline/_ref: its models + CPDtorch.utils.dist_util.sum_gradients "
-                       "+ CPDtorch.quant.float_quantize (NCCL all_gather + per-parameter elementwise kernels)"},
+            "dtype": DTYPE, "data": DATA, "impl": "reference", "config": shared_config(args.model, cfg, world, 1),
+            "impl_detail": {"path": "unmodified drcut/CPD from baseline/_ref: its models + CPDtorch.utils.dist_util.sum_gradients "
+                                    "+ CPDtorch.quant.float_quantize (NCCL all_gather + per-parameter elementwise kernels)"
+                                    + ("; every nn.Conv2d replaced by the reference's own Quant_Conv (F.unfold + tvm_gemm)"
+                                       if "gemm_exp" in cfg else "")},
             "e2e": {"value": round(value, 1), "unit": "images/s", "h2d_bytes_per_step": cfg["batch"] * (4 * cfg["shape"][0] * cfg["shape"][1] * cfg["shape"][2] + 8),
                     "d2h_bytes_per_step": 4, "note": "the reference step already includes the pinned H2D copy and the loss .item()"},
             "gpu_launches": 0, "clocks": clocks, "final_loss": round(losses[-1], 4),
@@ -248,6 +269,32 @@ def run_reference(args, cfg):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_allreduce_sweep(args):
+    """BASELINE.json config 5: low-bit all-reduce time / bus GB/s, 1 KB .. 1 GB of fp32 payload, fused variants vs plain
+    NCCL fp32 all-reduce vs the reference algorithm (all_gather + W x {add, quantize}), device-timed, max over ranks."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import torch
+    import torch.distributed as dist
+    import multigpu_check as mg
+    from cpd_b200 import dist_init
+    rank, world = dist_init()
+    res = {}
+    mg.section_sweep(rank, world, res, args.sweep_max_bytes, quiet=True)
+    if rank == 0:
+        rows = res["sweep"]
+        keep = ("fp32_bytes", "fused_auto_us", "fused_auto_busbw_fp32_GBps", "fused_auto_kahan_us", "fused_raw_us", "fused_oneshot_us",
+                "fused_twoshot_us", "fused_nvls_us", "nccl_fp32_allreduce_us", "nccl_fp32_busbw_GBps", "reference_algo_us",
+                "reference_algo_busbw_fp32_GBps", "fused_fp32_auto_us", "fused_fp32_auto_busbw_GBps", "fused_nvls_fast_us")
+        big = max(rows, key=lambda r: r["fp32_bytes"])
+        print(json.dumps({"metric": "low-bit all-reduce effective fp32 bus GB/s at the largest message ((4,3)+APS, fused, auto variant)",
+                          "value": big.get("fused_auto_busbw_fp32_GBps"), "unit": "GB/s", "n_gpus": world, "higher_is_better": True,
+                          "impl": "ours", "config": {"sweep": "1 KB .. %d B fp32 payload" % args.sweep_max_bytes, "format": "exp4man3+APS",
+                                                     "timing": "CUDA events, max over ranks, fresh gradient buffer per call"},
+                          "rows": [{k: r.get(k) for k in keep if k in r} for r in rows]}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 faulthandler.enable()
@@ -260,7 +307,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--model", choices=sorted(CONFIGS), default="resnet18")
-    ap.add_argument("--algo", default="auto", choices=["auto", "oneshot", "twoshot", "nvls", "nccl"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "oneshot", "twoshot", "nvls", "raw", "nvls_fast", "nccl"])
+    ap.add_argument("--allreduce-sweep", dest="allreduce_sweep", action="store_true",
+                    help="BASELINE config 5: all-reduce time / bus GB/s sweep instead of a training benchmark (needs --gpus >= 2)")
+    ap.add_argument("--sweep-max-bytes", dest="sweep_max_bytes", type=int, default=1 << 30)
     ap.add_argument("--overlap", action="store_true")
     ap.add_argument("--bucket-mb", dest="bucket_mb", type=float, default=0.0)
     ap.add_argument("--emulate-node", dest="emulate_node", type=int, default=1)
@@ -275,6 +325,12 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
     cfg = CONFIGS[args.model]
+    if args.allreduce_sweep:
+        if int(os.environ.get("WORLD_SIZE", "1")) < 2:
+            print(json.dumps({"metric": "allreduce sweep", "unavailable": "needs --gpus >= 2"}))
+            return
+        run_allreduce_sweep(args)
+        return
     if args.impl == "reference":
         run_reference(args, cfg)
     else:

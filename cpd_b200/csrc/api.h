@@ -94,19 +94,45 @@ void allreduce_fused_cuda(const CommBuffers& cb, float* grad, const Chunk* chunk
                           unsigned* local_ws /*barrier[2], epoch, status, amax[2][T]*/, int* shifts_out,
                           int max_ctas, unsigned long long timeout_cycles, cudaStream_t st);
 
+// Operand staging for the tensor-core GEMM (cuda/operand_stage_sm100.cu): gather + cast in one kernel.
+struct StageDesc {
+  const float* src;
+  long long base;          // element offset added to every address (flips start from the far end)
+  int mode;                // 0 = GATHER (strided, k split in three), 1 = IM2COL
+  int rows_fast;           // 1: the source is contiguous along the output ROW index (read r-fast), 0: along k
+  // GATHER: address = base + r * s_row + k1 * s1 + k2 * s2 + k3 * s3,  k = (k1 * n2 + k2) * n3 + k3
+  long long s_row, s1, s2, s3;
+  int n2, n3;
+  // IM2COL over x[b, ih, iw, c] with element strides (sb, sh, sw, sc): pixel = (b, oh, ow), tap = (kh, kw, c)
+  int taps_are_rows;       // 0: rows = pixels, k = taps;  1: rows = taps, k = pixels (transposed im2col)
+  int C, H, W, OH, OW, KH, KW, stride, pad, dil, in_dil;
+  long long sb, sh, sw, sc;
+};
+// operand_mode as in gemm_tc_cuda (0 bf16, 1 fp32/tf32, 2 e4m3, 3 e5m2); dst rows have Kp elements (Kp % 8 == 0)
+int operand_stage_cuda(const StageDesc& d, void* dst, long long R, long long K, long long Kp, int operand_mode, cudaStream_t st);
+// out[j] = Q(sum_i x[i*ld + j]) : the bias gradient of Quant_Linear / Quant_Conv
+void colsum_quantize_cuda(const float* x, long long rows, int cols, long long ld, float* out, int e, int m, int rounding,
+                          cudaStream_t st);
+
 // tcgen05 / TMEM / TMA GEMM with per-K-slice accumulator re-quantisation.
 // operand_mode: 0 = bf16 operands (kind::f16), 1 = tf32 (kind::tf32), 2 = e4m3, 3 = e5m2
 // variant: 0 = auto, 1 = 128x128 single-CTA tiles, 2 = 256x256 CTA-pair tiles (cta_group::2 cluster kernel,
 // packed 16-bit accumulators; formats (5,10), (8,7), (4,3), (5,2) only)
+// lda / ldb: row strides of A / Bt in ELEMENTS (0 = K; staged operands have padded rows, the TMA descriptor still
+// declares the true K so the tail is zero-filled in flight).  splits > 1: split-K — split z accumulates its own
+// contiguous range of K-slices into workspace[z] (fp32 [splits, M, N]); a second kernel folds the splits IN ORDER,
+// C = fold_z Q(C (+) part_z) (+ bias): the ordered low-precision fold of CPD applied across K ranges, which gives
+// the skinny weight-gradient GEMMs (reduction over batch x pixels) a grid that fills the machine.
 int gemm_tc_cuda(const void* A, const void* B, float* C, int M, int N, int K, int e, int m,
-                 bool kahan, int k_slice, int operand_mode, const float* bias, int variant, cudaStream_t st);
+                 bool kahan, int k_slice, int operand_mode, const float* bias, int variant, cudaStream_t st,
+                 long long lda = 0, long long ldb = 0, int splits = 1, float* workspace = nullptr);
 // MXFP8 operand staging: fp32 [R,K] -> fp8 codes [R,Kp] + UE8M0 per-32 block scales in the tcgen05 scale-factor atom layout
 void mx_quantize_cuda(const float* in, long long ld_in, uint8_t* codes, uint8_t* sf, int R, int K, int Kp, bool e5m2, cudaStream_t st);
 // block-scaled GEMM (tcgen05.mma.kind::mxf8f6f4.block_scale) with per-K-slice accumulator requant
 int gemm_tc_mx_cuda(const uint8_t* codes_a, const uint8_t* sf_a, const uint8_t* codes_b, const uint8_t* sf_b, float* C, int M, int N,
                     int Kp, int e, int m, bool kahan, int k_slice, bool e5m2, const float* bias, cudaStream_t st);
 int gemm_tc2_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, int e, int m, bool kahan, int k_slice,
-                  int operand_mode, const float* bias, cudaStream_t st);
+                  int operand_mode, const float* bias, cudaStream_t st, long long lda = 0, long long ldb = 0);
 #endif
 
 }  // namespace cpd

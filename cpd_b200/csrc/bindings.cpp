@@ -8,6 +8,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <atomic>
 #include <stdexcept>
 
 #include "api.h"
@@ -26,7 +27,11 @@ void check_fmt(int e, int m) {
   if (e < 1 || e > 8) throw std::invalid_argument("exp must be in [1, 8]");
   if (m < 0 || m > 23) throw std::invalid_argument("man must be in [0, 23]");
 }
+// every kernel launch of this library passes through check_launch(): the counter is what bench.py reports as
+// `gpu_launches` (counted, not estimated; launches recorded into a CUDA graph count once per capture)
+std::atomic<long long> g_launches{0};
 void check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) throw std::runtime_error(std::string("cpd_b200: ") + what + " launch failed: " + cudaGetErrorString(err));
 }
@@ -78,12 +83,43 @@ PYBIND11_MODULE(_C, m) {
   });
   // A [M,K] row-major, Bt [N,K] row-major (both K-major); operand_mode 0 bf16, 1 tf32(fp32 in), 2 e4m3, 3 e5m2
   m.def("gemm_tc_cuda", [](uptr A, uptr Bt, uptr C, int M, int N, int K, int e, int mb, bool kahan, int k_slice,
-                           int operand_mode, uptr bias, int variant, uptr stream) {
+                           int operand_mode, uptr bias, int variant, uptr stream, int64_t lda, int64_t ldb, int splits,
+                           uptr workspace) {
     check_fmt(e, mb);
     int rc = cpd::gemm_tc_cuda(P<const void>(A), P<const void>(Bt), P<float>(C), M, N, K, e, mb, kahan, k_slice, operand_mode,
-                               P<const float>(bias), variant, S(stream));
+                               P<const float>(bias), variant, S(stream), lda, ldb, splits, P<float>(workspace));
+    if (splits > 1 && rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);      // + the split-K fold kernel
     check_launch("gemm_tc");
     return rc;
+  }, py::arg("A"), py::arg("Bt"), py::arg("C"), py::arg("M"), py::arg("N"), py::arg("K"), py::arg("e"), py::arg("m"),
+     py::arg("kahan"), py::arg("k_slice"), py::arg("operand_mode"), py::arg("bias"), py::arg("variant"), py::arg("stream"),
+     py::arg("lda") = 0, py::arg("ldb") = 0, py::arg("splits") = 1, py::arg("workspace") = (uptr)0);
+
+  // operand staging: fp32 -> tensor-core operand (gather / im2col + cast), see cuda/operand_stage_sm100.cu
+  m.def("stage_gather_cuda", [](uptr src, int64_t base, int rows_fast, int64_t s_row, int64_t s1, int64_t s2, int64_t s3, int n2, int n3,
+                                uptr dst, int64_t R, int64_t K, int64_t Kp, int operand_mode, uptr stream) {
+    cpd::StageDesc d{};
+    d.src = P<const float>(src); d.base = base; d.mode = 0; d.rows_fast = rows_fast;
+    d.s_row = s_row; d.s1 = s1; d.s2 = s2; d.s3 = s3; d.n2 = n2 < 1 ? 1 : n2; d.n3 = n3 < 1 ? 1 : n3;
+    int rc = cpd::operand_stage_cuda(d, P<void>(dst), R, K, Kp, operand_mode, S(stream));
+    check_launch("operand_stage(gather)");
+    return rc;
+  });
+  m.def("stage_im2col_cuda", [](uptr src, int64_t base, int rows_fast, int taps_are_rows, int C, int H, int W, int OH, int OW, int KH, int KW,
+                                int stride, int pad, int dil, int in_dil, int64_t sb, int64_t sh, int64_t sw, int64_t sc,
+                                uptr dst, int64_t R, int64_t K, int64_t Kp, int operand_mode, uptr stream) {
+    cpd::StageDesc d{};
+    d.src = P<const float>(src); d.base = base; d.mode = 1; d.rows_fast = rows_fast; d.taps_are_rows = taps_are_rows;
+    d.C = C; d.H = H; d.W = W; d.OH = OH; d.OW = OW; d.KH = KH; d.KW = KW; d.stride = stride; d.pad = pad; d.dil = dil;
+    d.in_dil = in_dil < 1 ? 1 : in_dil; d.sb = sb; d.sh = sh; d.sw = sw; d.sc = sc; d.n2 = d.n3 = 1;
+    int rc = cpd::operand_stage_cuda(d, P<void>(dst), R, K, Kp, operand_mode, S(stream));
+    check_launch("operand_stage(im2col)");
+    return rc;
+  });
+  m.def("colsum_quantize_cuda", [](uptr x, int64_t rows, int cols, int64_t ld, uptr out, int e, int mb, int rounding, uptr stream) {
+    check_fmt(e, mb);
+    cpd::colsum_quantize_cuda(P<const float>(x), rows, cols, ld, P<float>(out), e, mb, rounding, S(stream));
+    check_launch("colsum_quantize");
   });
 
   m.def("mx_quantize_cuda", [](uptr in, int64_t ld_in, uptr codes, uptr sf, int R, int K, int Kp, bool e5m2, uptr stream) {
@@ -144,6 +180,8 @@ PYBIND11_MODULE(_C, m) {
   m.def("wire_bits", [](int e, int mb) { return cpd::wire_bits(e, mb); });
   m.def("chunk_struct_size", []() { return (int)sizeof(cpd::Chunk); });
   m.def("sm_count", [](int dev) { return cpd::device_sm_count(dev); });
+  m.def("launch_count", []() { return g_launches.load(std::memory_order_relaxed); },
+        "number of CUDA kernel-launching entry points of this library called so far in this process");
 
   // ------------------------------------------------------------------------ comm --
   m.def("discover_topology_json", &cpd::comm::discover_topology_json);
@@ -153,6 +191,7 @@ PYBIND11_MODULE(_C, m) {
       .def("open", &cpd::comm::SymmRegion::open, py::call_guard<py::gil_scoped_release>())
       .def("exchange", &cpd::comm::SymmRegion::exchange, py::call_guard<py::gil_scoped_release>())
       .def("bind_multicast", &cpd::comm::SymmRegion::bind_multicast, py::call_guard<py::gil_scoped_release>())
+      .def("close", &cpd::comm::SymmRegion::close_region, py::call_guard<py::gil_scoped_release>())
       .def("ptr", [](const cpd::comm::SymmRegion& r, int i) { return reinterpret_cast<uptr>(r.ptr(i)); })
       .def("mc_ptr", [](const cpd::comm::SymmRegion& r) { return reinterpret_cast<uptr>(r.mc_ptr()); })
       .def("bytes", &cpd::comm::SymmRegion::bytes)

@@ -37,6 +37,7 @@ class SymmRegion {
   void open();
   void exchange();
   void bind_multicast();
+  void close_region();      // collective teardown: unmap / unbind / release everything (caller barriers before and after)
   void* ptr(int r) const { return ptrs_[r]; }
   void* mc_ptr() const { return mc_ptr_; }
   size_t bytes() const { return bytes_; }
@@ -53,7 +54,7 @@ class SymmRegion {
   void* mc_ptr_ = nullptr;
   unsigned long long mc_handle_ = 0;
   int local_fd_ = -1, mc_fd_ = -1, listen_fd_ = -1;
-  bool mc_ok_ = false;
+  bool mc_ok_ = false, closed_ = false;
   std::string log_;
 };
 

@@ -62,6 +62,7 @@ using PFN_cuMemGetGranularity = CUresult (*)(size_t*, const CUmemAllocationProp*
 using PFN_cuMulticastCreate = CUresult (*)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*);
 using PFN_cuMulticastAddDevice = CUresult (*)(CUmemGenericAllocationHandle, CUdevice);
 using PFN_cuMulticastBindMem = CUresult (*)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long);
+using PFN_cuMulticastUnbind = CUresult (*)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t);
 using PFN_cuMulticastGetGranularity = CUresult (*)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags);
 using PFN_cuDeviceGet = CUresult (*)(CUdevice*, int);
 using PFN_cuDeviceGetAttribute = CUresult (*)(int*, CUdevice_attribute, CUdevice);
@@ -315,8 +316,49 @@ void SymmRegion::bind_multicast() {
   mc_ptr_ = reinterpret_cast<void*>(va);
 }
 
+// Collective teardown (the caller synchronises the device and barriers the group first: no kernel of any rank may
+// still touch a mapping): multicast view -> unbind -> multicast object, then every peer mapping and the local
+// allocation.  Errors are logged, not thrown: a half-released region must not take the training job down.
+void SymmRegion::close_region() {
+  if (closed_) return;
+  closed_ = true;
+  cudaSetDevice(device_);
+  cudaDeviceSynchronize();
+  PFN_cuMemUnmap cuMemUnmap_ = nullptr;
+  PFN_cuMemAddressFree cuMemAddressFree_ = nullptr;
+  PFN_cuMemRelease cuMemRelease_ = nullptr;
+  try {
+    cuMemUnmap_ = drv<PFN_cuMemUnmap>("cuMemUnmap");
+    cuMemAddressFree_ = drv<PFN_cuMemAddressFree>("cuMemAddressFree");
+    cuMemRelease_ = drv<PFN_cuMemRelease>("cuMemRelease");
+  } catch (const std::exception& e) { log_ += std::string("close: ") + e.what() + "; "; return; }
+  auto note = [&](CUresult r, const char* what) { if (r != CUDA_SUCCESS) log_ += std::string(what) + " failed (" + std::to_string((int)r) + "); "; };
+  if (mc_ptr_) {
+    const CUdeviceptr va = reinterpret_cast<CUdeviceptr>(mc_ptr_);
+    note(cuMemUnmap_(va, bytes_), "cuMemUnmap(mc)");
+    note(cuMemAddressFree_(va, bytes_), "cuMemAddressFree(mc)");
+    try {
+      auto cuMulticastUnbind_ = drv<PFN_cuMulticastUnbind>("cuMulticastUnbind");
+      auto cuDeviceGet_ = drv<PFN_cuDeviceGet>("cuDeviceGet");
+      CUdevice dev;
+      if (cuDeviceGet_(&dev, device_) == CUDA_SUCCESS) note(cuMulticastUnbind_(mc_handle_, dev, 0, bytes_), "cuMulticastUnbind");
+    } catch (const std::exception& e) { log_ += std::string("close: ") + e.what() + "; "; }
+    mc_ptr_ = nullptr;
+  }
+  if (mc_handle_) { note(cuMemRelease_(mc_handle_), "cuMemRelease(mc)"); mc_handle_ = 0; }
+  for (int r = 0; r < world_; ++r) {
+    if (ptrs_[r]) {
+      const CUdeviceptr va = reinterpret_cast<CUdeviceptr>(ptrs_[r]);
+      note(cuMemUnmap_(va, bytes_), "cuMemUnmap");
+      note(cuMemAddressFree_(va, bytes_), "cuMemAddressFree");
+      ptrs_[r] = nullptr;
+    }
+    if (handles_[r]) { note(cuMemRelease_(handles_[r]), "cuMemRelease"); handles_[r] = 0; }
+  }
+}
+
 SymmRegion::~SymmRegion() {
-  // Mappings live for the life of the process (training job); the driver reclaims them at exit.
+  // without an explicit (collective) close_region() the mappings live for the life of the process
   if (listen_fd_ >= 0) close(listen_fd_);
   if (local_fd_ >= 0) close(local_fd_);
   if (mc_fd_ >= 0) close(mc_fd_);

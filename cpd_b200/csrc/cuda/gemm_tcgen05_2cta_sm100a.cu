@@ -252,7 +252,7 @@ using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-bool make_tmap2(CUtensorMap* tm, const void* base, int rows, int K, int elem_bytes, CUtensorMapDataType dt, int box_rows) {
+bool make_tmap2(CUtensorMap* tm, const void* base, int rows, int K, long long ld, int elem_bytes, CUtensorMapDataType dt, int box_rows) {
   static PFN_encodeTiled enc = nullptr;
   if (!enc) {
     void* p = nullptr;
@@ -261,7 +261,7 @@ bool make_tmap2(CUtensorMap* tm, const void* base, int rows, int K, int elem_byt
     enc = reinterpret_cast<PFN_encodeTiled>(p);
   }
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)K * elem_bytes};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)(tc::STAGE_ROW_BYTES / elem_bytes), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return enc(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -299,8 +299,10 @@ int launch2_fmt(const CUtensorMap& ta, const CUtensorMap& tb, float* C, const fl
 
 // Returns 0 on launch, <0 if this kernel does not cover the request (the caller then uses the 1-CTA kernel).
 int gemm_tc2_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, int e, int m, bool kahan, int k_slice,
-                  int operand_mode, const float* bias, cudaStream_t st) {
+                  int operand_mode, const float* bias, cudaStream_t st, long long lda, long long ldb) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (lda <= 0) lda = K;
+  if (ldb <= 0) ldb = K;
   const bool packed = (e == 5 && m == 10) || (e == 8 && m == 7) || (e == 4 && m == 3) || (e == 5 && m == 2);
   if (!packed) return -5;
   int elem_bytes, kind;
@@ -313,13 +315,13 @@ int gemm_tc2_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, 
     case 3: elem_bytes = 1; kind = 2; fmt_code = 1; dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; break;
     default: return -1;
   }
-  if (((long long)K * elem_bytes) % 16 != 0) return -2;
+  if ((lda * elem_bytes) % 16 != 0 || (ldb * elem_bytes) % 16 != 0) return -2;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt)) & 15u) return -2;
   const int k_elems_per_block = tc::STAGE_ROW_BYTES / elem_bytes;
   int kbs = k_slice <= 0 ? (K + k_elems_per_block - 1) / k_elems_per_block : (k_slice + k_elems_per_block - 1) / k_elems_per_block;
   if (kbs < 1) kbs = 1;
   CUtensorMap ta, tb;
-  if (!make_tmap2(&ta, A, M, K, elem_bytes, dt, tc2::CTA_M) || !make_tmap2(&tb, Bt, N, K, elem_bytes, dt, tc2::CTA_BROWS)) return -4;
+  if (!make_tmap2(&ta, A, M, K, lda, elem_bytes, dt, tc2::CTA_M) || !make_tmap2(&tb, Bt, N, K, ldb, elem_bytes, dt, tc2::CTA_BROWS)) return -4;
   const uint32_t idesc = (1u << 4) | (fmt_code << 7) | (fmt_code << 10) | ((uint32_t)(tc2::BLOCK_N >> 3) << 17) |
                          ((uint32_t)(tc2::PAIR_M >> 4) << 24);
   if (kind == 0) return launch2_fmt<0>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, e, m, kahan, st);

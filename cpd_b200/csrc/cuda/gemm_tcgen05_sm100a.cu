@@ -63,7 +63,7 @@ template <int KIND, class F, bool KAHAN>
 __global__ void __launch_bounds__(tc::NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     float* __restrict__ C, const float* __restrict__ bias, int M, int N, int K, int elem_bytes,
-                    int kblocks_per_slice, uint32_t idesc, F fmt) {
+                    int kblocks_per_slice, uint32_t idesc, F fmt, int kblocks_per_split) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -74,8 +74,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
   const int k_elems_per_block = STAGE_ROW_BYTES / elem_bytes;
-  const int num_kblocks = (K + k_elems_per_block - 1) / k_elems_per_block;
+  const int total_kblocks = (K + k_elems_per_block - 1) / k_elems_per_block;
+  // split-K: this CTA owns K-blocks [kb0, kb0 + num_kblocks) and writes its own fp32 partial matrix
+  const int kb0 = blockIdx.z * kblocks_per_split;
+  const int num_kblocks = max(0, min(total_kblocks - kb0, kblocks_per_split));
   const int num_slices = (num_kblocks + kblocks_per_slice - 1) / kblocks_per_slice;
+  C += (long long)blockIdx.z * M * N;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -100,8 +104,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t ph = (kb / NUM_STAGES) & 1;
         mbar_wait(&bars->empty[s], ph ^ 1);
         mbar_expect_tx(&bars->full[s], A_STAGE_BYTES + B_STAGE_BYTES);
-        tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, &bars->full[s], kb * k_elems_per_block, m0);
-        tma_load_2d(smem_b + s * B_STAGE_BYTES, &tmap_b, &bars->full[s], kb * k_elems_per_block, n0);
+        tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, &bars->full[s], (kb0 + kb) * k_elems_per_block, m0);
+        tma_load_2d(smem_b + s * B_STAGE_BYTES, &tmap_b, &bars->full[s], (kb0 + kb) * k_elems_per_block, n0);
       }
     }
   } else if (warp == 1) {
@@ -216,32 +220,58 @@ PFN_encodeTiled get_encode() {
 }
 
 // 2-D row-major [rows, K] operand, box = {128 B of K, 128 rows}, 128B swizzle, zero fill out of bounds
-bool make_tmap(CUtensorMap* tm, const void* base, int rows, int K, int elem_bytes, CUtensorMapDataType dt) {
+bool make_tmap(CUtensorMap* tm, const void* base, int rows, int K, long long ld, int elem_bytes, CUtensorMapDataType dt) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
-  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)K * elem_bytes};
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};          // the TRUE K: the tail of the last box is zero-filled
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)(tc::STAGE_ROW_BYTES / elem_bytes), (cuuint32_t)tc::BLOCK_M};
   cuuint32_t estr[2] = {1, 1};
   return enc(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// C = fold_z Q(C (+) part_z) (+ bias): ordered low-precision fold of the split-K partials (each already a member of
+// the format: the splits' own last cast), same cast as the GEMM epilogue
+template <class F, bool KAHAN>
+__global__ void __launch_bounds__(256)
+splitk_fold_kernel(const float* __restrict__ parts, int splits, long long MN, int N, const float* __restrict__ bias,
+                   float* __restrict__ C, F fmt) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < MN; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f, c = 0.f;
+    for (int z = 0; z < splits; ++z) {
+      const float p = parts[(long long)z * MN + i];
+      if (KAHAN) fold_kahan(fmt, s, c, p);
+      else fold_plain(fmt, s, p);
+    }
+    C[i] = s + (bias ? bias[i % N] : 0.f);
+  }
+}
+
 template <int KIND>
 int launch_kind(const CUtensorMap& ta, const CUtensorMap& tb, float* C, const float* bias, int M, int N, int K, int elem_bytes,
-                int kblocks_per_slice, uint32_t idesc, int e, int m, bool kahan, cudaStream_t st) {
-  dim3 grid((N + tc::BLOCK_N - 1) / tc::BLOCK_N, (M + tc::BLOCK_M - 1) / tc::BLOCK_M);
+                int kblocks_per_slice, uint32_t idesc, int e, int m, bool kahan, cudaStream_t st, int splits, int kblocks_per_split,
+                float* workspace) {
+  dim3 grid((N + tc::BLOCK_N - 1) / tc::BLOCK_N, (M + tc::BLOCK_M - 1) / tc::BLOCK_M, splits);
+  float* out = splits > 1 ? workspace : C;
+  const float* kbias = splits > 1 ? nullptr : bias;
   int rc = 0;
   // accumulator casts use IEEE rounding (hardware F2F/F2FP converts for fp16/bf16/e4m3/e5m2-shaped formats)
   CPD_DISPATCH_FORMAT_IEEE_HW(e, m, FMT, {
     if (kahan) {
       auto kfn = gemm_tcgen05_kernel<KIND, decltype(FMT), true>;
       if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES) != cudaSuccess) rc = -3;
-      else kfn<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, FMT);
+      else kfn<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(ta, tb, out, kbias, M, N, K, elem_bytes, kblocks_per_slice, idesc, FMT, kblocks_per_split);
     } else {
       auto kfn = gemm_tcgen05_kernel<KIND, decltype(FMT), false>;
       if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES) != cudaSuccess) rc = -3;
-      else kfn<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, FMT);
+      else kfn<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(ta, tb, out, kbias, M, N, K, elem_bytes, kblocks_per_slice, idesc, FMT, kblocks_per_split);
+    }
+    if (rc == 0 && splits > 1) {
+      const long long MN = (long long)M * N;
+      const int fgrid = (int)((MN + 255) / 256 < 4096 ? (MN + 255) / 256 : 4096);
+      if (kahan) splitk_fold_kernel<decltype(FMT), true><<<fgrid, 256, 0, st>>>(workspace, splits, MN, N, bias, C, FMT);
+      else splitk_fold_kernel<decltype(FMT), false><<<fgrid, 256, 0, st>>>(workspace, splits, MN, N, bias, C, FMT);
     }
   });
   return rc;
@@ -251,12 +281,17 @@ int launch_kind(const CUtensorMap& ta, const CUtensorMap& tb, float* C, const fl
 
 // operand_mode: 0 bf16 (kind::f16), 1 fp32 read as tf32 (kind::tf32), 2 e4m3, 3 e5m2 (kind::f8f6f4)
 int gemm_tc_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, int e, int m, bool kahan, int k_slice,
-                 int operand_mode, const float* bias, int variant, cudaStream_t st) {
+                 int operand_mode, const float* bias, int variant, cudaStream_t st, long long lda, long long ldb, int splits,
+                 float* workspace) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (lda <= 0) lda = K;
+  if (ldb <= 0) ldb = K;
+  if (splits < 1) splits = 1;
+  if (splits > 1 && !workspace) return -6;
   // CTA-pair kernel when it covers the format and its 256x256 tiles still fill the machine
   // (Kahan's four casts per element make the kernel requant-bound either way; measured slightly faster on 128x128 tiles)
-  if (variant == 2 || (variant == 0 && !kahan && 2 * ((M + 255) / 256) * ((N + 255) / 256) >= device_sm_count(-1))) {
-    const int rc = gemm_tc2_cuda(A, Bt, C, M, N, K, e, m, kahan, k_slice, operand_mode, bias, st);
+  if (splits == 1 && (variant == 2 || (variant == 0 && !kahan && 2 * ((M + 255) / 256) * ((N + 255) / 256) >= device_sm_count(-1)))) {
+    const int rc = gemm_tc2_cuda(A, Bt, C, M, N, K, e, m, kahan, k_slice, operand_mode, bias, st, lda, ldb);
     if (rc == 0 || variant == 2) return rc;
   }
   int elem_bytes, kind;
@@ -269,20 +304,26 @@ int gemm_tc_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, i
     case 3: elem_bytes = 1; kind = 2; fmt_code = 1; dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; break;
     default: return -1;
   }
-  if (((long long)K * elem_bytes) % 16 != 0) return -2;       // TMA global stride must be a multiple of 16 B
+  if ((lda * elem_bytes) % 16 != 0 || (ldb * elem_bytes) % 16 != 0) return -2;       // TMA global stride must be a multiple of 16 B
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt)) & 15u) return -2;
   const int k_elems_per_block = tc::STAGE_ROW_BYTES / elem_bytes;
-  int kblocks_per_slice = k_slice <= 0 ? (K + k_elems_per_block - 1) / k_elems_per_block
-                                       : (k_slice + k_elems_per_block - 1) / k_elems_per_block;
+  const int total_kblocks = (K + k_elems_per_block - 1) / k_elems_per_block;
+  int kblocks_per_slice = k_slice <= 0 ? total_kblocks : (k_slice + k_elems_per_block - 1) / k_elems_per_block;
   if (kblocks_per_slice < 1) kblocks_per_slice = 1;
+  // every split owns whole K-slices, so the per-slice casts inside a split are those of the unsplit kernel
+  int slices = (total_kblocks + kblocks_per_slice - 1) / kblocks_per_slice;
+  if (splits > slices) splits = slices;
+  const int slices_per_split = (slices + splits - 1) / splits;
+  const int kblocks_per_split = slices_per_split * kblocks_per_slice;
+  splits = (total_kblocks + kblocks_per_split - 1) / kblocks_per_split;
   CUtensorMap ta, tb;
-  if (!make_tmap(&ta, A, M, K, elem_bytes, dt) || !make_tmap(&tb, Bt, N, K, elem_bytes, dt)) return -4;
+  if (!make_tmap(&ta, A, M, K, lda, elem_bytes, dt) || !make_tmap(&tb, Bt, N, K, ldb, elem_bytes, dt)) return -4;
   // instruction descriptor: D fp32 | A/B format | K-major both | N >> 3 | M >> 4
   const uint32_t idesc = (1u << 4) | (fmt_code << 7) | (fmt_code << 10) | ((uint32_t)(tc::BLOCK_N >> 3) << 17) |
                          ((uint32_t)(tc::BLOCK_M >> 4) << 24);
-  if (kind == 0) return launch_kind<0>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st);
-  if (kind == 1) return launch_kind<1>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st);
-  return launch_kind<2>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st);
+  if (kind == 0) return launch_kind<0>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st, splits, kblocks_per_split, workspace);
+  if (kind == 1) return launch_kind<1>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st, splits, kblocks_per_split, workspace);
+  return launch_kind<2>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st, splits, kblocks_per_split, workspace);
 }
 
 }  // namespace cpd

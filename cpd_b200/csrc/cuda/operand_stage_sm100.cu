@@ -1,0 +1,170 @@
+// operand_stage_sm100.cu — ONE kernel that turns an fp32 tensor into a tensor-core operand.
+//
+// The reference's custom-precision layers glue their GEMM together with torch ops
+// (CPDtorch/quant/quant_module.py:26-52,115-139 + quant_function.py:95-97): F.unfold (an fp32 im2col 9x the size of
+// the activations), transposes materialised by .contiguous(), a zero-filled output, a separate bias add.  Round 1 of
+// this repo kept that shape (pad + .to(dtype) + .t().contiguous() around the tcgen05 kernel).  This kernel replaces
+// all of it on the operand side: it gathers the logical matrix
+//        out[r][k],  r < R rows,  k < K reduction index        (row-major, row stride Kp >= K, K-major = what TMA wants)
+// from fp32 memory through one of two address generators, casts to the operand type of the tensor-core kind
+// (bf16 / fp32-as-tf32 / e4m3 / e5m2, saturating: an fp8 cast of |x| > 448 must not become NaN) and writes 16-byte
+// vectors.  Address generators:
+//   GATHER   k = (k1, k2, k3) with sizes (n1, n2, n3) and arbitrary (also negative) element strides, rows with their own
+//            stride: plain / transposed 2-D matrices, [O,C,KH,KW] weights viewed as [O,(kh,kw,c)], spatially flipped
+//            weights for the data-gradient, dy^T for the weight-gradient — no materialised transposes.
+//   IM2COL   rows <-> output pixels (b, oh, ow), k <-> filter taps (kh, kw, c) of a 2-D convolution over an activation
+//            tensor with arbitrary (NCHW or NHWC) strides, stride / padding / dilation and an optional input dilation
+//            (zero-upsampled dy of a strided convolution's data-gradient); `taps_are_rows` swaps the roles (the
+//            weight-gradient's B operand is the TRANSPOSED im2col matrix).  Out-of-image taps are zeros.
+// Tiles of 64 x 64 go through shared memory, so whichever of the two logical dimensions is contiguous in the source
+// is read coalesced and the destination is always written in whole 16-byte vectors along k.
+// K tails are NOT padded by anyone: the GEMM's TMA descriptor declares the true K and zero-fills out of bounds.
+// A second small kernel does the bias gradient, column sums of dy cast to (exp, man): quant_module.py:49-50.
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../api.h"
+#include "../common/fpformat.h"
+#include "format_dispatch.cuh"
+
+namespace cpd {
+
+namespace {
+
+constexpr int kTile = 64;
+constexpr int kStageThreads = 256;
+
+__device__ __forceinline__ float stage_fetch(const StageDesc& d, long long r, long long k) {
+  if (d.mode == 0) {
+    const long long n23 = (long long)d.n2 * d.n3;
+    const long long k1 = k / n23, rem = k - k1 * n23;
+    const long long k2 = rem / d.n3, k3 = rem - k2 * d.n3;
+    return d.src[d.base + r * d.s_row + k1 * d.s1 + k2 * d.s2 + k3 * d.s3];
+  }
+  const long long pix = d.taps_are_rows ? k : r, tap = d.taps_are_rows ? r : k;
+  const int ohw = d.OH * d.OW;
+  const int b = (int)(pix / ohw), prem = (int)(pix - (long long)b * ohw);
+  const int oh = prem / d.OW, ow = prem - oh * d.OW;
+  const int kwc = d.KW * d.C;
+  const int kh = (int)(tap / kwc), trem = (int)(tap - (long long)kh * kwc);
+  const int kw = trem / d.C, c = trem - kw * d.C;
+  int ih = oh * d.stride - d.pad + kh * d.dil, iw = ow * d.stride - d.pad + kw * d.dil;
+  if (d.in_dil > 1) {                                   // input dilation: only every in_dil-th coordinate carries data
+    if (ih < 0 || iw < 0 || ih % d.in_dil || iw % d.in_dil) return 0.f;
+    ih /= d.in_dil; iw /= d.in_dil;
+  }
+  if (ih < 0 || ih >= d.H || iw < 0 || iw >= d.W) return 0.f;
+  return d.src[d.base + (long long)b * d.sb + (long long)ih * d.sh + (long long)iw * d.sw + (long long)c * d.sc];
+}
+
+// 8 consecutive k of one row -> operand dtype, one vector store
+template <int OP>
+__device__ __forceinline__ void stage_store8(void* dst_row, int k, const float (&v)[8]) {
+  if (OP == 0) {                                                       // bf16
+    uint4 o;
+    __nv_bfloat162 h;
+    h = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst_row) + k) = o;
+  } else if (OP == 1) {                                                // fp32 (consumed as tf32)
+    float* p = reinterpret_cast<float*>(dst_row) + k;
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {                                                             // e4m3 / e5m2, saturating
+    constexpr __nv_fp8_interpretation_t I = OP == 2 ? __NV_E4M3 : __NV_E5M2;
+    uint2 o;
+    o.x = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(v[0], v[1]), __NV_SATFINITE, I) |
+          ((uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(v[2], v[3]), __NV_SATFINITE, I) << 16);
+    o.y = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(v[4], v[5]), __NV_SATFINITE, I) |
+          ((uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(v[6], v[7]), __NV_SATFINITE, I) << 16);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(dst_row) + k) = o;
+  }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kStageThreads)
+operand_stage_kernel(const StageDesc d, void* __restrict__ dst, long long R, long long K, long long Kp) {
+  __shared__ float tile[kTile][kTile + 1];
+  constexpr int ES = OP == 0 ? 2 : (OP == 1 ? 4 : 1);
+  const long long tiles_k = (Kp + kTile - 1) / kTile;
+  const long long n_tiles = ((R + kTile - 1) / kTile) * tiles_k;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const long long r0 = (t / tiles_k) * kTile, k0 = (t % tiles_k) * kTile;
+    // load phase: the source-contiguous dimension runs across the threads of a warp
+#pragma unroll 4
+    for (int i = 0; i < kTile * kTile / kStageThreads; ++i) {
+      const int lin = i * kStageThreads + threadIdx.x;
+      const int fast = lin % kTile, slow = lin / kTile;
+      const int rr = d.rows_fast ? fast : slow, kk = d.rows_fast ? slow : fast;
+      const long long r = r0 + rr, k = k0 + kk;
+      tile[rr][kk] = (r < R && k < K) ? stage_fetch(d, r, k) : 0.f;
+    }
+    __syncthreads();
+    // store phase: 8 consecutive k per thread, rows across the rest
+#pragma unroll
+    for (int j = 0; j < kTile * kTile / 8 / kStageThreads; ++j) {
+      const int lin = j * kStageThreads + threadIdx.x;
+      const int rr = lin / (kTile / 8), kg = (lin % (kTile / 8)) * 8;
+      const long long r = r0 + rr, k = k0 + kg;
+      if (r < R && k < Kp) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = tile[rr][kg + q];
+        stage_store8<OP>(reinterpret_cast<uint8_t*>(dst) + r * Kp * ES, (int)k, v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// grad_bias[j] = Q(sum_i dy[i][j])  (quant_module.py:49-50: float_quantize(grad_output.sum(0)))
+template <class F>
+__global__ void __launch_bounds__(256)
+colsum_quantize_kernel(const float* __restrict__ x, long long rows, int cols, long long ld, float* __restrict__ out, F fmt) {
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < cols)
+    for (long long r = ry; r < rows; r += 8) s += x[r * ld + c];
+  part[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x & 31];
+    out[c] = fmt.q(t);
+  }
+}
+
+}  // namespace
+
+int operand_stage_cuda(const StageDesc& d, void* dst, long long R, long long K, long long Kp, int operand_mode, cudaStream_t st) {
+  if (R <= 0 || K <= 0) return 0;
+  if (Kp < K || Kp % 8) return -1;                       // rows are written in 8-element vectors
+  const long long n_tiles = ((R + kTile - 1) / kTile) * ((Kp + kTile - 1) / kTile);
+  const long long cap = (long long)device_sm_count(-1) * 8;
+  const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+  switch (operand_mode) {
+    case 0: operand_stage_kernel<0><<<grid, kStageThreads, 0, st>>>(d, dst, R, K, Kp); break;
+    case 1: operand_stage_kernel<1><<<grid, kStageThreads, 0, st>>>(d, dst, R, K, Kp); break;
+    case 2: operand_stage_kernel<2><<<grid, kStageThreads, 0, st>>>(d, dst, R, K, Kp); break;
+    case 3: operand_stage_kernel<3><<<grid, kStageThreads, 0, st>>>(d, dst, R, K, Kp); break;
+    default: return -2;
+  }
+  return 0;
+}
+
+void colsum_quantize_cuda(const float* x, long long rows, int cols, long long ld, float* out, int e, int m, int rounding,
+                          cudaStream_t st) {
+  if (cols <= 0) return;
+  CPD_DISPATCH_FORMAT(e, m, rounding, FMT, {
+    colsum_quantize_kernel<decltype(FMT)><<<(cols + 31) / 32, 256, 0, st>>>(x, rows, cols, ld, out, FMT);
+  });
+}
+
+}  // namespace cpd

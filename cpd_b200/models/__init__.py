@@ -1,9 +1,10 @@
-from .resnet_cifar import resnet18_cifar, resnet34_cifar, ResNetCifar  # noqa: F401
+from .resnet_cifar import resnet18_cifar, resnet34_cifar, resnet18_cifar_quant, ResNetCifar  # noqa: F401
 from .resnet_imagenet import resnet18, resnet34, resnet50, resnet101, ResNet  # noqa: F401
 from .davidnet import davidnet, GraphNet, graph_from_nested, rel, Identity, Concat, Correct, Scale, Add, batch_norm  # noqa: F401
 
 _REGISTRY = {
     "resnet18_cifar": resnet18_cifar, "res_cifar": resnet18_cifar, "resnet34_cifar": resnet34_cifar,
+    "resnet18_cifar_quant": resnet18_cifar_quant,
     "resnet18": resnet18, "resnet34": resnet34, "resnet50": resnet50, "resnet101": resnet101,
     "davidnet": davidnet,
 }

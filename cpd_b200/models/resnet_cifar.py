@@ -8,22 +8,22 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
-def _conv3x3(cin, cout, stride=1):
-    return nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False)
+def _plain_conv(cin, cout, k, stride=1, padding=0):
+    return nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=False)
 
 
 class BasicBlock(nn.Module):
     expansion = 1
 
-    def __init__(self, cin: int, cout: int, stride: int = 1):
+    def __init__(self, cin: int, cout: int, stride: int = 1, conv=_plain_conv):
         super().__init__()
-        self.conv1 = _conv3x3(cin, cout, stride)
+        self.conv1 = conv(cin, cout, 3, stride=stride, padding=1)
         self.bn1 = nn.BatchNorm2d(cout)
-        self.conv2 = _conv3x3(cout, cout)
+        self.conv2 = conv(cout, cout, 3, stride=1, padding=1)
         self.bn2 = nn.BatchNorm2d(cout)
         self.proj = None
         if stride != 1 or cin != cout:
-            self.proj = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False), nn.BatchNorm2d(cout))
+            self.proj = nn.Sequential(conv(cin, cout, 1, stride=stride, padding=0), nn.BatchNorm2d(cout))
 
     def forward(self, x):
         y = F.relu(self.bn1(self.conv1(x)), inplace=True)
@@ -35,13 +35,13 @@ class BasicBlock(nn.Module):
 class ResNetCifar(nn.Module):
     """CIFAR ResNet of the reference (resnet18_cifar.py): 3x3 stem without max-pool, 4 stages of BasicBlocks,
     ``avg_pool2d(4)``, linear head; ``forward(x, rank=None)`` keeps the reference's unused ``rank`` argument."""
-    def __init__(self, blocks=(2, 2, 2, 2), widths=(64, 128, 256, 512), num_classes: int = 10):
+    def __init__(self, blocks=(2, 2, 2, 2), widths=(64, 128, 256, 512), num_classes: int = 10, conv=_plain_conv):
         super().__init__()
-        self.stem = nn.Sequential(_conv3x3(3, widths[0]), nn.BatchNorm2d(widths[0]), nn.ReLU(inplace=True))
+        self.stem = nn.Sequential(conv(3, widths[0], 3, stride=1, padding=1), nn.BatchNorm2d(widths[0]), nn.ReLU(inplace=True))
         stages, cin = [], widths[0]
         for i, (n, w) in enumerate(zip(blocks, widths)):
             for j in range(n):
-                stages.append(BasicBlock(cin, w, stride=(2 if (i > 0 and j == 0) else 1)))
+                stages.append(BasicBlock(cin, w, stride=(2 if (i > 0 and j == 0) else 1), conv=conv))
                 cin = w
         self.stages = nn.Sequential(*stages)
         self.fc = nn.Linear(cin, num_classes)
@@ -58,3 +58,18 @@ def resnet18_cifar(num_classes: int = 10) -> ResNetCifar:
 
 def resnet34_cifar(num_classes: int = 10) -> ResNetCifar:
     return ResNetCifar((3, 4, 6, 3), num_classes=num_classes)
+
+
+def resnet18_cifar_quant(num_classes: int = 10, exp: int = 5, man: int = 10, mode: str = "tile", operands=None, k_slice: int = 128,
+                         kahan: bool = False) -> ResNetCifar:
+    """The same network with EVERY convolution a ``Quant_Conv`` (CPDtorch/quant/quant_module.py:88-139): forward,
+    data-gradient and weight-gradient GEMMs keep their accumulator at (exp, man).  ``mode="tile"`` runs them on the
+    tcgen05 kernels with fused im2col/cast staging, ``"exact"`` is the reference's per-MAC semantics.  The 10-class
+    head stays ``nn.Linear``: the reference's GEMM is unreliable for outputs with fewer than 16 rows (its remainder
+    branch), so the comparison arm cannot quantise it either."""
+    from ..quant import Quant_Conv
+
+    def conv(cin, cout, k, stride=1, padding=0):
+        return Quant_Conv(cin, cout, k, stride=stride, padding=padding, bias=False, exp=exp, man=man, mode=mode,
+                          operands=operands, k_slice=k_slice, kahan=kahan)
+    return ResNetCifar((2, 2, 2, 2), num_classes=num_classes, conv=conv)

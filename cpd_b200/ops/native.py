@@ -143,31 +143,117 @@ OPERAND_BF16, OPERAND_TF32, OPERAND_E4M3, OPERAND_E5M2 = 0, 1, 2, 3
 GEMM_AUTO, GEMM_1CTA, GEMM_2CTA = 0, 1, 2
 
 
+_OPERAND_TORCH = {OPERAND_BF16: torch.bfloat16, OPERAND_TF32: torch.float32, OPERAND_E4M3: torch.float8_e4m3fn,
+                  OPERAND_E5M2: torch.float8_e5m2}
+
+
 def gemm_tc(a: torch.Tensor, bt: torch.Tensor, exp: int, man: int, kahan: bool = False, k_slice: int = 128,
             operand_mode: int = OPERAND_BF16, bias: Optional[torch.Tensor] = None,
-            out: Optional[torch.Tensor] = None, variant: int = GEMM_AUTO) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, variant: int = GEMM_AUTO, k: Optional[int] = None,
+            splits: int = 1) -> torch.Tensor:
     """tcgen05 GEMM: C[M,N] = A[M,K] @ Bt[N,K]^T, accumulator re-quantised to (exp,man)
     (IEEE rounding) after every K-slice.  Operands must already be in the operand dtype (bf16 /
-    fp32 for tf32 / float8).  ``variant``: auto | 128x128 single-CTA tiles | 256x256 CTA-pair
-    (cluster, cta_group::2) tiles with packed 16-bit accumulators."""
+    fp32 for tf32 / float8), K-major with unit inner stride; rows may be padded (``k`` = the true K, the TMA
+    descriptor zero-fills the tail).  ``variant``: auto | 128x128 single-CTA tiles | 256x256 CTA-pair
+    (cluster, cta_group::2) tiles with packed 16-bit accumulators.  ``splits`` > 1: split-K with an ordered
+    quantised fold of the partial matrices (skinny outputs with a long reduction, e.g. weight gradients)."""
     _check_fmt(exp, man)
-    if not (a.is_cuda and bt.is_cuda and a.is_contiguous() and bt.is_contiguous()):
-        raise ValueError("gemm_tc: contiguous CUDA operands expected")
-    want = {OPERAND_BF16: torch.bfloat16, OPERAND_TF32: torch.float32, OPERAND_E4M3: torch.float8_e4m3fn,
-            OPERAND_E5M2: torch.float8_e5m2}[operand_mode]
+    if not (a.is_cuda and bt.is_cuda and a.dim() == 2 and bt.dim() == 2 and a.stride(1) == 1 and bt.stride(1) == 1):
+        raise ValueError("gemm_tc: 2-D CUDA operands with unit inner stride expected")
+    want = _OPERAND_TORCH[operand_mode]
     if a.dtype != want or bt.dtype != want:
         raise TypeError(f"gemm_tc: operand_mode {operand_mode} needs {want}, got {a.dtype}/{bt.dtype}")
-    M, K = a.shape
-    N = bt.shape[0]
-    if bt.shape[1] != K:
+    M, N = a.shape[0], bt.shape[0]
+    K = int(k) if k is not None else a.shape[1]
+    if K > a.shape[1] or K > bt.shape[1] or (k is None and bt.shape[1] != K):
         raise ValueError("gemm_tc: K mismatch")
+    lda, ldb = (a.stride(0) if M > 1 else a.shape[1]), (bt.stride(0) if N > 1 else bt.shape[1])
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    ws = None
+    splits = max(1, int(splits))
+    if splits > 1:
+        ws = torch.empty(splits, M, N, dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         rc = _C.gemm_tc_cuda(a.data_ptr(), bt.data_ptr(), out.data_ptr(), M, N, K, int(exp), int(man), bool(kahan),
-                             int(k_slice), int(operand_mode), _ptr(bias), int(variant), _stream(a))
+                             int(k_slice), int(operand_mode), _ptr(bias), int(variant), _stream(a), int(lda), int(ldb),
+                             splits, _ptr(ws))
     if rc != 0:
         raise RuntimeError(f"gemm_tc: kernel rejected the problem (code {rc})")
+    return out
+
+
+# ---- operand staging: gather / im2col + cast in one kernel (cuda/operand_stage_sm100.cu) -----------------------------
+def _staged_empty(R: int, K: int, operand_mode: int, device) -> torch.Tensor:
+    Kp = (K + 15) // 16 * 16           # 16-byte rows for every operand type (TMA global stride)
+    return torch.empty(R, Kp, dtype=_OPERAND_TORCH[operand_mode], device=device)
+
+
+def stage_gather(src: torch.Tensor, R: int, sizes, strides, s_row: int, operand_mode: int, base: int = 0,
+                 rows_fast: Optional[bool] = None) -> torch.Tensor:
+    """out[r, k] = src.flat[base + r * s_row + k1 * s1 + k2 * s2 + k3 * s3], k = (k1, k2, k3) row-major over ``sizes``,
+    cast to the operand dtype; returns [R, Kp] (use ``[:, :K]`` / pass ``k=K`` to gemm_tc).  Strides are in elements of
+    ``src``'s storage view and may be negative."""
+    _f32(src, "src")
+    if not src.is_cuda:
+        raise ValueError("stage_gather: CUDA tensor expected")
+    n1, n2, n3 = [int(v) for v in sizes]
+    s1, s2, s3 = [int(v) for v in strides]
+    K = n1 * n2 * n3
+    if rows_fast is None:
+        rows_fast = abs(int(s_row)) == 1 and abs(s3) != 1
+    out = _staged_empty(R, K, operand_mode, src.device)
+    with torch.cuda.device(src.device):
+        rc = _C.stage_gather_cuda(src.data_ptr(), int(base), int(bool(rows_fast)), int(s_row), s1, s2, s3, n2, n3,
+                                  out.data_ptr(), R, K, out.shape[1], int(operand_mode), _stream(src))
+    if rc != 0:
+        raise RuntimeError(f"stage_gather: rejected (code {rc})")
+    return out
+
+
+def stage_matrix(x: torch.Tensor, operand_mode: int) -> torch.Tensor:
+    """Any 2-D fp32 view (transposed, sliced, ...) -> K-major operand [R, Kp]: no materialised transpose, no pad."""
+    if x.dim() != 2:
+        raise ValueError("stage_matrix: 2-D tensor expected")
+    return stage_gather(x, x.shape[0], (1, 1, x.shape[1]), (0, 0, x.stride(1)), x.stride(0), operand_mode)
+
+
+def stage_im2col(x: torch.Tensor, kh: int, kw: int, out_hw, stride: int, pad: int, dil: int, operand_mode: int,
+                 in_dil: int = 1, taps_are_rows: bool = False) -> torch.Tensor:
+    """im2col of x[B, C, H, W] (any strides: NCHW or channels_last) fused with the operand cast:
+    rows = output pixels (b, oh, ow), k = taps (kh, kw, c)  [taps_are_rows: the transposed matrix].  ``in_dil`` > 1
+    treats x as zero-upsampled by that factor (data-gradient of a strided convolution)."""
+    _f32(x, "x")
+    if not x.is_cuda or x.dim() != 4:
+        raise ValueError("stage_im2col: 4-D CUDA tensor expected")
+    B, C, H, W = x.shape
+    OH, OW = int(out_hw[0]), int(out_hw[1])
+    pixels, taps = B * OH * OW, kh * kw * C
+    R, K = (taps, pixels) if taps_are_rows else (pixels, taps)
+    sb, sc, sh, sw = x.stride()
+    # which logical dimension is contiguous in the source?  channels_last: c = the fastest TAP index; NCHW: iw ~ the
+    # fastest PIXEL index.  The kernel reads that dimension across the threads of a warp.
+    chan_fast = sc == 1 and C > 1
+    rows_fast = chan_fast == bool(taps_are_rows)
+    out = _staged_empty(R, K, operand_mode, x.device)
+    with torch.cuda.device(x.device):
+        rc = _C.stage_im2col_cuda(x.data_ptr(), 0, int(rows_fast), int(bool(taps_are_rows)), C, H, W, OH, OW, int(kh), int(kw),
+                                  int(stride), int(pad), int(dil), int(in_dil), sb, sh, sw, sc,
+                                  out.data_ptr(), R, K, out.shape[1], int(operand_mode), _stream(x))
+    if rc != 0:
+        raise RuntimeError(f"stage_im2col: rejected (code {rc})")
+    return out
+
+
+def colsum_quantize(x2d: torch.Tensor, exp: int, man: int, rounding=ROUND_REF) -> torch.Tensor:
+    """Q(x.sum(0)) of a row-major [rows, cols] fp32 view with unit column stride: the bias gradient in one launch."""
+    _f32(x2d, "x"); _check_fmt(exp, man)
+    if not x2d.is_cuda or x2d.dim() != 2 or x2d.stride(1) != 1:
+        raise ValueError("colsum_quantize: 2-D CUDA tensor with unit inner stride expected")
+    out = torch.empty(x2d.shape[1], dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        _C.colsum_quantize_cuda(x2d.data_ptr(), x2d.shape[0], x2d.shape[1], x2d.stride(0) if x2d.shape[0] > 1 else x2d.shape[1],
+                                out.data_ptr(), int(exp), int(man), rounding_code(rounding), _stream(x2d))
     return out
 
 

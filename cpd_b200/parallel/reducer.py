@@ -368,6 +368,14 @@ class GradReducer:
         c = self.local_ws[base:base + 2].cpu().tolist()
         return {"nonfinite_tensor_events": int(c[0]), "all_zero_tensor_events": int(c[1])}
 
+    def close(self) -> None:
+        """Release the symmetric workspace (collective: every rank calls it).  The reducer is unusable afterwards."""
+        self.remove_hooks()
+        if self.symm is not None:
+            self.symm.close()
+            self.symm = None
+            self.mode = "closed"
+
     def remove_hooks(self) -> None:
         for h in self._hooks:
             h.remove()

@@ -86,6 +86,28 @@ class SymmetricWorkspace:
     def has_multicast(self) -> bool:
         return bool(self.mc_base)
 
+    def close(self) -> None:
+        """Collective teardown: every rank of the group must call it, after its last kernel on the region.  Device sync
+        + barrier (no rank may still read a peer mapping), release (vmm: unmap / multicast unbind / handle release;
+        ipc: close peer handles, free), barrier.  Idempotent."""
+        if self.ptrs is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        for item in self._keep:
+            if isinstance(item, tuple) and item[0] == "ipc":
+                for r, p in enumerate(self.ptrs):
+                    if r != self.rank:
+                        _C.ipc_close(p)
+                _C.ipc_free(item[1])
+            elif hasattr(item, "close") and hasattr(item, "bind_multicast"):
+                item.close()
+                if item.log():
+                    self.log.append("close: " + item.log())
+        self._keep = []
+        self.ptrs, self.buffers, self.mc_base = None, None, 0
+        dist.barrier(group=self.group)
+
     # -- backends -------------------------------------------------------------------
     def _agree(self, step, what: str):
         """Run ``step`` on every rank; raise on ALL ranks if it failed on any (keeps the

@@ -14,7 +14,7 @@ import torch
 
 from ..ops import native
 
-__all__ = ["float_quantize", "quantizer", "quant_gemm"]
+__all__ = ["float_quantize", "quantizer", "quant_gemm", "set_default_gemm_mode", "tile_gemm"]
 
 
 def float_quantize(x: torch.Tensor, exp: int, man: int, rounding: str = "reference", inplace: bool = False,
@@ -63,10 +63,26 @@ def quantizer(forward_exp: int = 8, forward_man: int = 23, backward_exp: int = 8
 
 
 # ---- GEMM ------------------------------------------------------------------------
+_DEFAULT_GEMM_MODE = "exact"
+
+
+def set_default_gemm_mode(mode: str) -> None:
+    """Process-wide default of ``quant_gemm`` / ``Quant_Linear`` / ``Quant_Conv`` when no ``mode`` is given:
+    "exact" (reference semantics, the default — also through the CPDtorch facade), "tile" (tensor cores) or "auto"."""
+    global _DEFAULT_GEMM_MODE
+    if mode not in ("exact", "tile", "auto"):
+        raise ValueError(f"unknown gemm mode {mode!r}")
+    _DEFAULT_GEMM_MODE = mode
+
+
 _TILE_MIN_WORK = 1 << 24      # M*N*K above which the tensor-core kernel takes over in mode="auto"
 
 
-def _operand_mode(exp: int, man: int) -> int:
+def operand_mode_for(exp: int, man: int, operands: Optional[str] = None) -> int:
+    """Tensor-core operand type of the tile mode: fp8 for the fp8-shaped accumulator formats, bf16 up to 7 mantissa
+    bits, tf32 above; or what ``operands`` names."""
+    if operands:
+        return _OPERAND_NAME[operands]
     if (exp, man) == (4, 3):
         return native.OPERAND_E4M3
     if (exp, man) == (5, 2):
@@ -76,26 +92,59 @@ def _operand_mode(exp: int, man: int) -> int:
     return native.OPERAND_TF32
 
 
-_OPERAND_DTYPE = {native.OPERAND_BF16: torch.bfloat16, native.OPERAND_TF32: torch.float32,
-                  native.OPERAND_E4M3: torch.float8_e4m3fn, native.OPERAND_E5M2: torch.float8_e5m2}
 _OPERAND_NAME = {"bf16": native.OPERAND_BF16, "tf32": native.OPERAND_TF32, "e4m3": native.OPERAND_E4M3,
                  "e5m2": native.OPERAND_E5M2}
 
 
-def quant_gemm(a: torch.Tensor, b: torch.Tensor, man: int = 23, exp: int = 8, mode: str = "auto",
+def resolve_gemm_mode(mode: Optional[str], is_cuda: bool, work: int) -> str:
+    mode = os.environ.get("CPD_B200_GEMM_MODE", mode or _DEFAULT_GEMM_MODE)
+    if mode == "auto":
+        mode = "tile" if (is_cuda and work >= _TILE_MIN_WORK) else "exact"
+    if mode not in ("exact", "tile"):
+        raise ValueError(f"unknown gemm mode {mode!r}")
+    return mode
+
+
+def splits_for(M: int, N: int, K: int, k_slice: int) -> int:
+    """Split-K factor of the tile mode: skinny outputs with a long reduction (weight gradients: [out_ch, taps] over
+    batch x pixels) get enough K ranges to fill the 148 SMs; each split keeps >= 4 K-slices."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    slices = max(1, (K + max(k_slice, 1) - 1) // max(k_slice, 1)) if k_slice > 0 else 1
+    if tiles >= 96 or slices < 8:
+        return 1
+    return max(1, min(64, 148 // tiles, slices // 4))
+
+
+def tile_gemm(a_view: torch.Tensor, bt_view: torch.Tensor, exp: int, man: int, kahan: bool = False, k_slice: int = 128,
+              operands: Optional[str] = None, bias: Optional[torch.Tensor] = None, splits: Optional[int] = None) -> torch.Tensor:
+    """C = a_view @ bt_view^T for two fp32 2-D VIEWS of any strides, on the tensor cores: each operand goes through ONE
+    staging launch (strided gather + cast to the operand type, K-major), the K tail is zero-filled by the TMA
+    descriptor, the bias is added in the GEMM epilogue.  No pad / .to() / .contiguous() / transposed copies."""
+    om = operand_mode_for(exp, man, operands)
+    M, K = a_view.shape
+    N = bt_view.shape[0]
+    a_op = native.stage_matrix(a_view, om)
+    b_op = native.stage_matrix(bt_view, om)
+    if splits is None:
+        splits = splits_for(M, N, K, k_slice)
+    return native.gemm_tc(a_op, b_op, exp, man, bool(kahan), k_slice, om, bias, k=K, splits=splits)
+
+
+def quant_gemm(a: torch.Tensor, b: torch.Tensor, man: int = 23, exp: int = 8, mode: Optional[str] = None,
                kahan: Optional[bool] = None, k_slice: int = 128, operands: Optional[str] = None,
                rounding: str = "reference", bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``a[M,K] @ b[K,N]`` with the accumulator held at (exp, man).  NB: ``man`` before
     ``exp``, as in the reference (quant_function.py:78).
 
-    mode="exact": the reference's semantics — strictly sequential k, every product and
+    mode="exact" (default): the reference's semantics — strictly sequential k, every product and
         every (Kahan) intermediate cast; SIMT kernel / C++ on CPU.  Inputs are not cast.
     mode="tile":  B200 throughput path — tcgen05 tensor-core partial sums over ``k_slice``
         elements of K in fp32 (TMEM), then ``s = Q(s (+) Q(partial))`` per slice with IEEE
-        rounding (hardware converts); operands are staged as fp8 for (4,3)/(5,2), bf16 for
-        man<=7, tf32 otherwise.  Large problems in the 16-bit-representable formats run on
-        CTA pairs (thread-block clusters, cta_group::2) with packed 16-bit accumulators.
-    mode="auto":  exact on CPU and for small problems, tile otherwise.
+        rounding (hardware converts).  This mode DOES cast the operands (saturating): fp8 for
+        (4,3)/(5,2), bf16 for man<=7, tf32 otherwise — numerics differ from "exact" by design,
+        which is why it is opt-in (``mode=``, ``set_default_gemm_mode``, env CPD_B200_GEMM_MODE).
+        Operands are staged by one fused gather+cast launch each (no pad / transposed copies).
+    mode="auto":  exact on CPU and below 2^24 multiply-adds, tile otherwise.
     ``operands``: "bf16" | "tf32" | "e4m3" | "e5m2" | "mxe4m3" | "mxe5m2" (block-scaled fp8: one
     UE8M0 scale per 32 K-elements, tcgen05 kind::mxf8f6f4.block_scale); default by format.
     ``kahan`` defaults to True for exact (as the reference) and False for tile.
@@ -103,31 +152,22 @@ def quant_gemm(a: torch.Tensor, b: torch.Tensor, man: int = 23, exp: int = 8, mo
     assert len(a.shape) == 2
     assert len(b.shape) == 2
     assert a.shape[1] == b.shape[0]
-    mode = os.environ.get("CPD_B200_GEMM_MODE", mode)
     M, K = a.shape
     N = b.shape[1]
-    if mode == "auto":
-        mode = "tile" if (a.is_cuda and M * N * K >= _TILE_MIN_WORK) else "exact"
+    mode = resolve_gemm_mode(mode, a.is_cuda, M * N * K)
     if mode == "exact":
         out = native.gemm_exact(a, b, exp, man, rounding, True if kahan is None else kahan)
         if bias is not None:
             out += bias
         return out
-    if mode != "tile":
-        raise ValueError(f"unknown gemm mode {mode!r}")
     if not a.is_cuda:
         raise NotImplementedError("mode='tile' needs a CUDA device (use ops.native.gemm_tile_cpu for the CPU model)")
-    if K % 16:      # TMA needs 16-byte aligned rows: zero-pad K (e.g. the 3x3x3 = 27 wide im2col of a first conv layer)
-        padk = 16 - K % 16
-        a = torch.nn.functional.pad(a, (0, padk))
-        b = torch.nn.functional.pad(b, (0, 0, 0, padk))
     if operands in ("mxe4m3", "mxe5m2"):       # block-scaled fp8 operands (one power-of-two scale per 32 K-elements)
         e5 = operands == "mxe5m2"
+        if K % 16:
+            a = torch.nn.functional.pad(a, (0, 16 - K % 16))
+            b = torch.nn.functional.pad(b, (0, 0, 0, 16 - K % 16))
         ac, asf = native.mx_quantize(a.contiguous(), e5)
         bc, bsf = native.mx_quantize(b.t().contiguous(), e5)
         return native.gemm_tc_mx(ac, asf, bc, bsf, exp, man, bool(kahan) if kahan is not None else False, k_slice, e5, bias)
-    om = _OPERAND_NAME[operands] if operands else _operand_mode(exp, man)
-    dt = _OPERAND_DTYPE[om]
-    a_op = a.to(dt).contiguous()
-    bt_op = b.t().to(dt).contiguous()           # [N, K], K-major: no copy if b is itself a transposed view
-    return native.gemm_tc(a_op, bt_op, exp, man, bool(kahan) if kahan is not None else False, k_slice, om, bias)
+    return tile_gemm(a, b.t(), exp, man, bool(kahan) if kahan is not None else False, k_slice, operands, bias)

@@ -10,9 +10,11 @@ import torch.nn.init as init
 from torch.autograd import Function
 from torch.nn.parameter import Parameter
 
-from .functional import float_quantize, quant_gemm, quantizer
+from .functional import (float_quantize, quant_gemm, quantizer, resolve_gemm_mode, operand_mode_for, splits_for,
+                         tile_gemm)
+from ..ops import native
 
-__all__ = ["Quantizer", "Quant_Linear", "Quant_Conv", "Quant_LinearFunction"]
+__all__ = ["Quantizer", "Quant_Linear", "Quant_Conv", "Quant_LinearFunction", "Quant_ConvTileFunction"]
 
 
 class Quantizer(nn.Module):
@@ -32,13 +34,17 @@ class Quantizer(nn.Module):
 
 class Quant_LinearFunction(Function):
     """y = x W^T (+ b) with all three GEMMs (fwd, dgrad, wgrad) accumulating at (exp, man)
-    (quant_module.py:23-52).  Transposes are passed as strided views — the kernels consume
-    them in place, the reference materialises them."""
+    (quant_module.py:23-52).  Transposes are never materialised: the exact kernel takes strided views, the tile mode
+    stages each operand with one gather+cast launch; the bias rides in the tensor-core epilogue and the bias gradient
+    is one column-reduce+cast launch."""
 
     @staticmethod
-    def forward(ctx, input, weight, bias=None, exp=8, man=23, mode="auto"):
+    def forward(ctx, input, weight, bias=None, exp=8, man=23, mode=None):
+        mode = resolve_gemm_mode(mode, input.is_cuda, input.shape[0] * weight.shape[0] * weight.shape[1])
         ctx.save_for_backward(input, weight, bias)
         ctx.exp, ctx.man, ctx.mode = exp, man, mode
+        if mode == "tile":
+            return tile_gemm(input, weight, exp, man, bias=bias)              # bias added in the epilogue (fp32, un-quantised)
         output = quant_gemm(input, weight.t(), man=man, exp=exp, mode=mode)
         if bias is not None:
             output += bias.unsqueeze(0).expand_as(output)      # fp32, un-quantised, as the reference
@@ -48,19 +54,87 @@ class Quant_LinearFunction(Function):
     def backward(ctx, grad_output):
         input, weight, bias = ctx.saved_tensors
         grad_input = grad_weight = grad_bias = None
+        tile = ctx.mode == "tile"
         if ctx.needs_input_grad[0]:
-            grad_input = quant_gemm(grad_output, weight, man=ctx.man, exp=ctx.exp, mode=ctx.mode)
+            grad_input = tile_gemm(grad_output, weight.t(), ctx.exp, ctx.man) if tile else \
+                quant_gemm(grad_output, weight, man=ctx.man, exp=ctx.exp, mode=ctx.mode)
         if ctx.needs_input_grad[1]:
-            grad_weight = quant_gemm(grad_output.t(), input, man=ctx.man, exp=ctx.exp, mode=ctx.mode)
+            grad_weight = tile_gemm(grad_output.t(), input.t(), ctx.exp, ctx.man) if tile else \
+                quant_gemm(grad_output.t(), input, man=ctx.man, exp=ctx.exp, mode=ctx.mode)
         if bias is not None and ctx.needs_input_grad[2]:
-            grad_bias = float_quantize(grad_output.sum(0), ctx.exp, ctx.man)
+            if grad_output.is_cuda and grad_output.stride(1) == 1:
+                grad_bias = native.colsum_quantize(grad_output, ctx.exp, ctx.man)
+            else:
+                grad_bias = float_quantize(grad_output.sum(0), ctx.exp, ctx.man)
         return grad_input, grad_weight, grad_bias, None, None, None
+
+
+class Quant_ConvTileFunction(Function):
+    """2-D convolution whose three GEMMs run on the tensor cores with the accumulator at (exp, man), WITHOUT the
+    reference's glue (quant_module.py:115-139: F.unfold's fp32 column matrix, transposed copies, separate bias add and
+    reshapes; autograd's col2im for the data gradient):
+
+      forward   y[(b,oh,ow), o]   = im2col(x)[(b,oh,ow), (kh,kw,c)]  .  W[o, (kh,kw,c)]^T   (+ bias in the epilogue)
+      dgrad     dx[(b,h,w), c]    = im2col'(dy)[(b,h,w), (kh,kw,o)]  .  Wflip[c, (kh,kw,o)]^T     (transposed conv:
+                                    taps of the zero-upsampled dy, spatially flipped filter — no col2im scatter)
+      wgrad     dW[o, (kh,kw,c)]  = dy^T[o, (b,oh,ow)]  .  im2col(x)^T[(kh,kw,c), (b,oh,ow)]^T   (split-K + ordered fold)
+
+    every operand is produced by ONE fused gather/im2col+cast launch from the fp32 tensor in whatever layout it has
+    (NCHW or channels_last), the outputs are channels_last views of the GEMM results (no permute copies).  4 launches
+    forward (2 staging + GEMM; bias fused), backward 3 + 4 (+1 bias gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, exp, man, stride, padding, dilation, k_slice, operands, kahan):
+        B, C, H, W = x.shape
+        O, _, KH, KW = weight.shape
+        OH = (H + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
+        OW = (W + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
+        om = operand_mode_for(exp, man, operands)
+        a = native.stage_im2col(x, KH, KW, (OH, OW), stride, padding, dilation, om)
+        ws = weight.stride()
+        bt = native.stage_gather(weight, O, (KH, KW, C), (ws[2], ws[3], ws[1]), ws[0], om)
+        K = KH * KW * C
+        y = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, bias, k=K)                      # [B*OH*OW, O] == NHWC
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (exp, man, stride, padding, dilation, k_slice, om, kahan, bias is not None, (OH, OW))
+        return y.view(B, OH, OW, O).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        exp, man, stride, padding, dilation, k_slice, om, kahan, has_bias, (OH, OW) = ctx.cfg
+        B, C, H, W = x.shape
+        O, _, KH, KW = weight.shape
+        dx = dw = db = None
+        ws = weight.stride()
+        if ctx.needs_input_grad[0]:
+            pad_t = dilation * (KH - 1) - padding
+            a = native.stage_im2col(dy, KH, KW, (H, W), 1, pad_t, dilation, om, in_dil=stride)          # [(b,h,w), (kh,kw,o)]
+            base = (KH - 1) * ws[2] + (KW - 1) * ws[3]
+            bt = native.stage_gather(weight, C, (KH, KW, O), (-ws[2], -ws[3], ws[0]), ws[1], om, base=base)   # flipped filter
+            g = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, None, k=KH * KW * O)             # [(b,h,w), c] == NHWC
+            dx = g.view(B, H, W, C).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            ds = dy.stride()
+            Mred = B * OH * OW
+            a = native.stage_gather(dy, O, (B, OH, OW), (ds[0], ds[2], ds[3]), ds[1], om)               # dy^T  [o, (b,oh,ow)]
+            bt = native.stage_im2col(x, KH, KW, (OH, OW), stride, padding, dilation, om, taps_are_rows=True)   # [(kh,kw,c), pixels]
+            K = KH * KW * C
+            g = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, None, k=Mred, splits=splits_for(O, K, Mred, k_slice))
+            dw = g.view(O, KH, KW, C).permute(0, 3, 1, 2)
+        if has_bias and ctx.needs_input_grad[2]:
+            if dy.stride(1) == 1 and dy.stride(3) == O and dy.stride(2) == O * OW and dy.stride(0) == O * OW * OH:
+                db = native.colsum_quantize(dy.permute(0, 2, 3, 1).reshape(-1, O), exp, man)
+            else:
+                db = float_quantize(dy.sum((0, 2, 3)), exp, man)
+        return dx, dw, db, None, None, None, None, None, None, None, None
 
 
 class Quant_Linear(nn.Module):
     """``nn.Linear`` whose forward and backward GEMMs keep their accumulator at (exp, man) (quant_module.py:55-85):
-    ``mode="exact"`` = the reference's per-MAC casts, ``"tile"`` = tensor cores with a cast per K-slice, ``"auto"`` by size."""
-    def __init__(self, in_features, out_features, bias=True, exp=8, man=23, mode="auto"):
+    ``mode="exact"`` (default) = the reference's per-MAC casts, ``"tile"`` = tensor cores with a cast per K-slice (casts
+    the operands too: opt-in), ``"auto"`` by size; ``None`` follows ``set_default_gemm_mode``."""
+    def __init__(self, in_features, out_features, bias=True, exp=8, man=23, mode=None):
         super().__init__()
         self.in_features, self.out_features = in_features, out_features
         self.exp, self.man, self.mode = exp, man, mode
@@ -95,7 +169,7 @@ class Quant_Conv(nn.Module):
     accepts ``dilation``/``groups`` but silently ignores them)."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
-                 bias=True, exp=8, man=23, mode="auto"):
+                 bias=True, exp=8, man=23, mode=None, k_slice=128, operands=None, kahan=False):
         super().__init__()
         if groups != 1:
             raise NotImplementedError("Quant_Conv: groups != 1 is not supported")
@@ -103,6 +177,7 @@ class Quant_Conv(nn.Module):
         self.kernel_size = (kernel_size, kernel_size)
         self.stride, self.padding, self.dilation = stride, padding, dilation
         self.exp, self.man, self.mode = exp, man, mode
+        self.k_slice, self.operands, self.kahan = k_slice, operands, kahan       # tile mode only
         self.weight = Parameter(torch.empty(out_channels, in_channels, kernel_size, kernel_size))
         self.bias = Parameter(torch.empty(out_channels)) if bias else None
         self.reset_parameters()
@@ -119,9 +194,13 @@ class Quant_Conv(nn.Module):
         k = self.kernel_size[0]
         oh = (h + 2 * self.padding - self.dilation * (k - 1) - 1) // self.stride + 1
         ow = (w + 2 * self.padding - self.dilation * (k - 1) - 1) // self.stride + 1
+        mode = resolve_gemm_mode(self.mode, input.is_cuda, batch * oh * ow * self.out_channels * self.in_channels * k * k)
+        if mode == "tile":
+            return Quant_ConvTileFunction.apply(input, self.weight, self.bias, self.exp, self.man, self.stride, self.padding,
+                                                self.dilation, self.k_slice, self.operands, self.kahan)
         cols = F.unfold(input, self.kernel_size, dilation=self.dilation, padding=self.padding, stride=self.stride)
         a = cols.transpose(1, 2).reshape(batch * oh * ow, -1)                  # [B*L, C*k*k]
-        y = Quant_LinearFunction.apply(a, self.weight.view(self.out_channels, -1), self.bias, self.exp, self.man, self.mode)
+        y = Quant_LinearFunction.apply(a, self.weight.reshape(self.out_channels, -1), self.bias, self.exp, self.man, mode)
         return y.view(batch, oh * ow, self.out_channels).transpose(1, 2).reshape(batch, self.out_channels, oh, ow)
 
     def extra_repr(self):

@@ -95,6 +95,15 @@ class TrainEngine:
         return F.cross_entropy(logits, target, reduction=red)
 
     def _step_body(self) -> None:
+        from ..ops import native
+        launches0 = native._C.launch_count()
+        try:
+            self._step_body_inner()
+        finally:
+            # cpd_b200 kernel launches of ONE step (counted by the native library); a captured graph replays exactly these
+            self.kernel_launches_per_step = int(native._C.launch_count() - launches0)
+
+    def _step_body_inner(self) -> None:
         nvtx = torch.cuda.nvtx if (self.is_cuda and _NVTX) else None
         self.loss_dev.zero_()
         denom = float(self.world * self.E)

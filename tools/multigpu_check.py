@@ -165,6 +165,7 @@ def section_correct(rank, world, res):
                     continue
                 fused = GradReducer(arena, PrecisionConfig(algo=algo, **kw), mode="fused")
                 if algo == "nvls" and not fused.symm.has_multicast:
+                    fused.close()
                     continue
                 ok = True
                 for rep in range(3):
@@ -177,6 +178,7 @@ def section_correct(rank, world, res):
                 shifts_ok = bool(torch.equal(fused.shifts[0], oracle.shifts[0])) if kw.get("use_aps") else True
                 out.append(dict(layout=lname, case=kw, algo=algo, wire=fused.wire, backend=fused.symm.backend, match=ok,
                                 ranks_identical=ident, shifts=shifts_ok))
+                fused.close()
                 del fused
             del oracle
     res["correct"] = out
@@ -192,6 +194,7 @@ def section_stress(rank, world, res, iters):
     for algo in ("oneshot", "twoshot", "nvls"):
         fused = GradReducer(big, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, bucket_mb=0.2, algo=algo), mode="fused")
         if algo == "nvls" and not fused.symm.has_multicast:
+            fused.close()
             continue
         fill(big, rank, seed=99)
         mine = big.grad_flat.clone()
@@ -209,6 +212,7 @@ def section_stress(rank, world, res, iters):
         fused.check_status()
         bad += 0 if same_bits(big.grad_flat, want) else 1
         out[algo] = dict(iters=iters, buckets=len(fused.buckets), mismatching_checks=bad, seconds=round(time.time() - t0, 2))
+        fused.close()
         del fused
     res["stress"] = out
     res["stress_all_pass"] = all(v["mismatching_checks"] == 0 for v in out.values())
@@ -246,6 +250,7 @@ def section_fault(rank, world, res):
         t = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         out[algo] = dict(all_on_time_ranks_raised_and_poisoned=bool(t.item()), rank0_error=msg if rank == 0 else None)
+        red.close()
         del red
         dist.barrier()
     res["fault"] = out
@@ -263,7 +268,7 @@ def reference_algorithm(g, world, e, m, gather_buf):
     g.copy_(res)
 
 
-def section_sweep(rank, world, res, max_bytes):
+def section_sweep(rank, world, res, max_bytes, quiet=False):
     dev = torch.device("cuda", torch.cuda.current_device())
     rows = []
     sizes = [1 << k for k in range(10, 31, 2) if (1 << k) <= max_bytes]       # fp32 payload bytes
@@ -298,6 +303,7 @@ def section_sweep(rank, world, res, max_bytes):
                 continue
             red = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, algo=algo), mode="fused")
             if algo == "nvls" and not red.symm.has_multicast:
+                red.close()
                 continue
             refill()
             ms = time_calls(lambda: red.reduce(next_buf()), iters)
@@ -311,6 +317,7 @@ def section_sweep(rank, world, res, max_bytes):
                 g = arena.grad_flat
                 ms = time_calls_restored(lambda: red.reduce(), lambda: g.copy_(orig), max(iters // 2, 4))
                 row[f"fused_{algo}_same_buffer_us"] = round(ms * 1e3, 2)
+            red.close()
             del red
         for kname, kalgo in (("auto", "auto"),):
             redk = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, use_kahan=True, algo=kalgo), mode="fused")
@@ -322,7 +329,25 @@ def section_sweep(rank, world, res, max_bytes):
             ms = time_calls(lambda: redp.reduce(next_buf()), iters)
             row[f"fused_{kname}_us"] = round(ms * 1e3, 2)
             row[f"fused_{kname}_busbw_fp32_GBps"] = round(nbytes / (ms * 1e-3) * 2 * (world - 1) / world / 1e9, 2)
+            redk.close(); redp.close()
             del redk, redp
+        # plain fp32 sum: the (8,23) path.  Reference = NCCL all_reduce (dist_util.py:55-59); ours = in-switch multimem.ld_reduce
+        redf = GradReducer(arena, PrecisionConfig(grad_exp=8, grad_man=23), mode="fused")
+        refill()
+        ms = time_calls(lambda: redf.reduce(next_buf()), iters)
+        row["fused_fp32_auto_us"] = round(ms * 1e3, 2)
+        row["fused_fp32_auto_algo"] = int(redf.algo_for(redf.buckets[0]))
+        row["fused_fp32_auto_busbw_GBps"] = round(nbytes / (ms * 1e-3) * 2 * (world - 1) / world / 1e9, 2)
+        redf.close()
+        del redf
+        # opt-in, NOT bit-exact: fp8 codes summed inside the switch with an fp16 accumulator
+        redq = GradReducer(arena, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, algo="nvls_fast"), mode="fused")
+        if redq.symm.has_multicast and nbytes >= (1 << 16):
+            refill()
+            ms = time_calls(lambda: redq.reduce(next_buf()), iters)
+            row["fused_nvls_fast_us"] = round(ms * 1e3, 2)
+        redq.close()
+        del redq
         refill()
         ms = time_calls(lambda: dist.all_reduce(next_buf()), iters)
         row["nccl_fp32_allreduce_us"] = round(ms * 1e3, 2)
@@ -340,7 +365,7 @@ def section_sweep(rank, world, res, max_bytes):
             del gb
         del pool, orig
         rows.append(row)
-        if rank == 0:
+        if rank == 0 and not quiet:
             print(json.dumps(row), flush=True)
         del arena
         torch.cuda.empty_cache()
