@@ -32,7 +32,7 @@ void gemm_exact_cpu(const float* A, int64_t sa0, int64_t sa1, const float* B, in
 // an operand format), then s = Q(s (+) Q(partial)) per slice.
 void gemm_tile_cpu(const float* A, int64_t sa0, int64_t sa1, const float* B, int64_t sb0, int64_t sb1,
                    float* C, int64_t ldc, int M, int N, int K, int e, int m, int rounding, bool kahan,
-                   int k_slice, int op_e, int op_m);
+                   int k_slice, int op_e, int op_m, int splits = 1);
 // APS + rank-ordered (Kahan) fold over W source buffers that share one segment table.
 void aps_fold_cpu(const float* const* srcs, int W, float* out, const int64_t* seg_off, int T,
                   int e, int m, int rounding, bool use_aps, bool kahan, float world_mult,

@@ -68,11 +68,11 @@ PYBIND11_MODULE(_C, m) {
     cpd::gemm_exact_cpu(P<const float>(A), sa0, sa1, P<const float>(B), sb0, sb1, P<float>(C), ldc, M, N, K, e, mb, rounding, kahan);
   });
   m.def("gemm_tile_cpu", [](uptr A, int64_t sa0, int64_t sa1, uptr B, int64_t sb0, int64_t sb1, uptr C, int64_t ldc, int M,
-                            int N, int K, int e, int mb, int rounding, bool kahan, int k_slice, int op_e, int op_m) {
+                            int N, int K, int e, int mb, int rounding, bool kahan, int k_slice, int op_e, int op_m, int splits) {
     check_fmt(e, mb);
     py::gil_scoped_release nogil;
     cpd::gemm_tile_cpu(P<const float>(A), sa0, sa1, P<const float>(B), sb0, sb1, P<float>(C), ldc, M, N, K, e, mb, rounding, kahan,
-                       k_slice, op_e, op_m);
+                       k_slice, op_e, op_m, splits);
   });
   m.def("gemm_exact_cuda", [](uptr A, int64_t sa0, int64_t sa1, uptr B, int64_t sb0, int64_t sb1, uptr C, int64_t ldc, int M,
                               int N, int K, int e, int mb, int rounding, bool kahan, uptr stream) {

@@ -34,6 +34,13 @@ struct FoldOps {
   static __device__ __forceinline__ uint32_t encode4(const F& f, const float (&x)[4]) {
     return f.pack(x[0]) | (f.pack(x[1]) << 8) | (f.pack(x[2]) << 16) | (f.pack(x[3]) << 24);
   }
+  // N values: x <- Q(x * sc), reference cast (the first cast of a raw gradient: quirk B can trigger, so the fold's
+  // exact-sum shortcut does not apply)
+  template <int N>
+  static __device__ __forceinline__ void qscaled_n(const F& f, float (&x)[N], float sc) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = f.q_wide(x[i] * sc);
+  }
   // scale + cast + pack of one granule in one step: only the hardware formats have it
   static __device__ __forceinline__ bool pack16_scaled(const F&, const float (&)[16], float, uint32_t (&)[4]) { return false; }
   static __device__ __forceinline__ void decode16(const F& f, const uint32_t (&w)[4], float (&x)[16]) {
@@ -89,6 +96,31 @@ struct FoldOpsFp8 {
       for (int i = 0; i < N; ++i) x[i] = qsum_cold(x[i]);
     }
   }
+  // N values: x <- Q(x * sc) with the REFERENCE cast through the conversion hardware: pretruncate() clears the bits the
+  // reference's truncating subnormal shift discards, after which the IEEE convert is the reference cast (proven on all
+  // 2^32 patterns below the overflow band, tests/cpp); NaN / Inf / overflow-band groups take the software cast.
+  template <int N>
+  static __device__ __forceinline__ void qscaled_n(const F& f, float (&x)[N], float sc) {
+    static_assert(N % 2 == 0, "pairs");
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] *= sc;
+    float g = fabsf(x[0]);
+#pragma unroll
+    for (int i = 1; i < N; ++i) asm("max.NaN.f32 %0, %0, %1;" : "+f"(g) : "f"(fabsf(x[i])));
+    if (g < kLimit) {
+#pragma unroll
+      for (int i = 0; i < N; i += 2) {
+        const __nv_fp8x2_storage_t c = __nv_cvt_float2_to_fp8x2(
+            make_float2(pretruncate<E_BITS, M_BITS>(x[i]), pretruncate<E_BITS, M_BITS>(x[i + 1])), __NV_SATFINITE, INTERP);
+        const float2 r = __half22float2(__half2(__nv_cvt_fp8x2_to_halfraw2(c, INTERP)));
+        x[i] = r.x; x[i + 1] = r.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] = qsum_cold_wide(x[i]);
+    }
+  }
+  static __device__ __noinline__ float qsum_cold_wide(float x) { return FormatT<E_BITS, M_BITS>::q_wide(x); }
   static __device__ __forceinline__ void decode4(const F& f, uint32_t w, float (&o)[4]) {
     if ((((w & kExpMask32) + kCarry32) & 0x80808080u) == 0u) {          // no reserved (all-ones exponent) code among the 4
       const __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w & 0xFFFFu), INTERP);

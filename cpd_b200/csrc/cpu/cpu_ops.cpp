@@ -77,37 +77,54 @@ void gemm_exact_cpu(const float* A, int64_t sa0, int64_t sa1, const float* B, in
 
 void gemm_tile_cpu(const float* A, int64_t sa0, int64_t sa1, const float* B, int64_t sb0, int64_t sb1,
                    float* C, int64_t ldc, int M, int N, int K, int e, int m, int rounding, bool kahan,
-                   int k_slice, int op_e, int op_m) {
+                   int k_slice, int op_e, int op_m, int splits) {
   const Format f = make_format(e, m, rounding);
   const Format fo = make_format(op_e, op_m, ROUND_IEEE);
   const bool round_ops = !(op_e == 8 && op_m == 23);
   FmtR q{f};
   if (k_slice <= 0) k_slice = K;
+  // split-K as the tensor-core launcher partitions it: whole K-slices per split, every split accumulates from zero,
+  // then the splits are folded IN ORDER with the same cast (C = fold_z Q(C (+) part_z))
+  const int slices = (K + k_slice - 1) / k_slice;
+  if (splits < 1) splits = 1;
+  if (splits > slices) splits = slices;
+  const int slices_per_split = (slices + splits - 1) / splits;
+  const int64_t k_per_split = (int64_t)slices_per_split * k_slice;
+  splits = (int)((K + k_per_split - 1) / k_per_split);
   const int64_t grain = std::max<int64_t>(1, (1 << 14) / std::max<int64_t>(1, (int64_t)N * K));
   parallel_for(M, grain, [=](int64_t r0, int64_t r1) {
   for (int64_t i = r0; i < r1; ++i) {
-    std::vector<float> s(N, 0.f), c(N, 0.f);
+    std::vector<float> tot(N, 0.f), totc(N, 0.f);
     std::vector<double> part(N);
-    for (int k0 = 0; k0 < K; k0 += k_slice) {
-      const int k1 = std::min(K, k0 + k_slice);
-      std::fill(part.begin(), part.end(), 0.0);
-      for (int k = k0; k < k1; ++k) {
-        float a = A[i * sa0 + k * sa1];
-        if (round_ops) a = quantize(a, fo);
-        const float* brow = B + (int64_t)k * sb0;
+    for (int z = 0; z < splits; ++z) {
+      std::vector<float> s(N, 0.f), c(N, 0.f);
+      const int kz0 = (int)(z * k_per_split), kz1 = (int)std::min<int64_t>(K, (z + 1) * k_per_split);
+      for (int k0 = kz0; k0 < kz1; k0 += k_slice) {
+        const int k1 = std::min(kz1, k0 + k_slice);
+        std::fill(part.begin(), part.end(), 0.0);
+        for (int k = k0; k < k1; ++k) {
+          float a = A[i * sa0 + k * sa1];
+          if (round_ops) a = quantize(a, fo);
+          const float* brow = B + (int64_t)k * sb0;
+          for (int j = 0; j < N; ++j) {
+            float b = brow[j * sb1];
+            if (round_ops) b = quantize(b, fo);
+            part[j] += (double)a * (double)b;    // stands in for the tensor core's wide accumulate
+          }
+        }
         for (int j = 0; j < N; ++j) {
-          float b = brow[j * sb1];
-          if (round_ops) b = quantize(b, fo);
-          part[j] += (double)a * (double)b;    // stands in for the tensor core's wide accumulate
+          const float p = q.q((float)part[j]);
+          if (kahan) fold_kahan(q, s[j], c[j], p);
+          else fold_plain(q, s[j], p);
         }
       }
+      if (splits == 1) { tot = s; break; }
       for (int j = 0; j < N; ++j) {
-        const float p = q.q((float)part[j]);
-        if (kahan) fold_kahan(q, s[j], c[j], p);
-        else fold_plain(q, s[j], p);
+        if (kahan) fold_kahan(q, tot[j], totc[j], s[j]);
+        else fold_plain(q, tot[j], s[j]);
       }
     }
-    for (int j = 0; j < N; ++j) C[i * ldc + j] = s[j];
+    for (int j = 0; j < N; ++j) C[i * ldc + j] = tot[j];
   }
   });
 }

@@ -125,15 +125,15 @@ def gemm_exact(a: torch.Tensor, b: torch.Tensor, exp: int, man: int, rounding=RO
     return out
 
 
-def gemm_tile_cpu(a, b, exp, man, rounding=ROUND_REF, kahan=False, k_slice=128, op_exp=8, op_man=23):
-    """CPU model of the tensor-core kernel's semantics (per-K-slice requantisation)."""
+def gemm_tile_cpu(a, b, exp, man, rounding=ROUND_REF, kahan=False, k_slice=128, op_exp=8, op_man=23, splits=1):
+    """CPU model of the tensor-core kernel's semantics (per-K-slice requantisation; split-K = ordered fold of the splits)."""
     _f32(a, "a"); _f32(b, "b"); _check_fmt(exp, man)
     M, K = a.shape
     N = b.shape[1]
     out = torch.empty(M, N, dtype=torch.float32)
     _C.gemm_tile_cpu(a.data_ptr(), a.stride(0), a.stride(1), b.data_ptr(), b.stride(0), b.stride(1), out.data_ptr(),
                      out.stride(0), M, N, K, int(exp), int(man), rounding_code(rounding), bool(kahan), int(k_slice),
-                     int(op_exp), int(op_man))
+                     int(op_exp), int(op_man), int(splits))
     return out
 
 

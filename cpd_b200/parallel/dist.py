@@ -106,8 +106,12 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def dist_init(backend: Optional[str] = None, timeout_s: int = 600, verbose: bool = False) -> Tuple[int, int]:
-    """Initialise ``torch.distributed`` and return ``(rank, world_size)`` like the reference."""
+def dist_init(backend: Optional[str] = None, timeout_s: int = 600, verbose: bool = False,
+              calibrate: Optional[bool] = None) -> Tuple[int, int]:
+    """Initialise ``torch.distributed`` and return ``(rank, world_size)`` like the reference.  On GPUs the box's
+    topology is discovered (it sets the all-reduce variant thresholds); ``calibrate=True`` (or env
+    CPD_B200_CALIBRATE=1) additionally measures the variants on the live group once and installs the measured
+    thresholds (parallel/calibrate.py, ~1 s)."""
     if dist.is_available() and dist.is_initialized():
         _STATE.update(rank=dist.get_rank(), world_size=dist.get_world_size())
         return _STATE["rank"], _STATE["world_size"]
@@ -134,6 +138,13 @@ def dist_init(backend: Optional[str] = None, timeout_s: int = 600, verbose: bool
         topo = discover_topology()
         if verbose and info["rank"] == 0:
             print(f"[cpd_b200] launcher={info['launcher']} world={info['world_size']} backend={backend}; {topo.summary()}")
+        if calibrate is None:
+            calibrate = os.environ.get("CPD_B200_CALIBRATE", "0") == "1"
+        if calibrate and info["world_size"] > 1 and backend == "nccl":
+            from .calibrate import calibrate as _calibrate
+            th = _calibrate(verbose=verbose)
+            if verbose and info["rank"] == 0:
+                print(f"[cpd_b200] calibrated all-reduce thresholds: {th.to_dict()}")
     return info["rank"], info["world_size"]
 
 

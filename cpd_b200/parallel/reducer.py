@@ -105,7 +105,7 @@ class GradReducer:
     the reference algorithm on NCCL/Gloo (all_gather + one fold launch; fallback and oracle), "local" = world size 1.
     Buckets follow ``cfg.bucket_mb``; with ``cfg.overlap`` they launch from gradient hooks on a comm stream."""
     def __init__(self, arena: ModelArena, cfg: PrecisionConfig, group=None, mode: Optional[str] = None,
-                 timeout_cycles: int = DEFAULT_TIMEOUT_CYCLES, thresholds: Optional[Thresholds] = None):
+                 timeout_cycles: int = DEFAULT_TIMEOUT_CYCLES, thresholds: Optional[Thresholds] = None, symm=None):
         self.arena = arena
         self.cfg = cfg
         self.group = group
@@ -158,6 +158,7 @@ class GradReducer:
 
         self.local_ws = None
         self.symm = None
+        self._owns_symm = True
         self._gather_buf = None
         if self.is_cuda:
             self.local_ws = torch.zeros(4 + 2 * MAX_TENSORS_PER_BUCKET + 32, dtype=torch.int32, device=self.device)
@@ -167,7 +168,13 @@ class GradReducer:
             if cfg.algo == "raw":
                 cap = self.max_numel * 4
             try:
-                self.symm = SymmetricWorkspace(cap, MAX_TENSORS_PER_BUCKET, group=group)
+                if symm is not None:                       # a caller-owned workspace (calibration, tools): must be big enough
+                    if symm.cap_bytes < cap:
+                        raise ValueError(f"shared symmetric workspace too small: {symm.cap_bytes} < {cap} bytes")
+                    self.symm, self._owns_symm = symm, False
+                else:
+                    self.symm = SymmetricWorkspace(cap, MAX_TENSORS_PER_BUCKET, group=group)
+                self.local_ws = self.symm.local_ws          # epoch / status / barrier words belong to the workspace
             except RuntimeError as err:
                 # no peer-memory backend (no P2P, > 8 ranks, ...): every rank fails together (the bring-up agrees on
                 # each step collectively), so an auto-selected fused mode degrades to the reference algorithm on NCCL
@@ -372,7 +379,8 @@ class GradReducer:
         """Release the symmetric workspace (collective: every rank calls it).  The reducer is unusable afterwards."""
         self.remove_hooks()
         if self.symm is not None:
-            self.symm.close()
+            if self._owns_symm:
+                self.symm.close()
             self.symm = None
             self.mode = "closed"
 

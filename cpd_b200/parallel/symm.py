@@ -79,6 +79,10 @@ class SymmetricWorkspace:
             [p + self.off_mailbox for p in ptrs], [p + self.off_flags for p in ptrs],
             (self.mc_base + self.off_gather) if self.mc_base else 0, self.cap_bytes, self.max_tensors,
             (self.mc_base + self.off_data) if self.mc_base else 0)
+        # device-local protocol state of THIS workspace (grid barrier, launch epoch, status word, amax[2][T], stamps):
+        # the epoch must live with the flags it is compared against, so every reducer that drives this workspace
+        # shares it
+        self.local_ws = torch.zeros(4 + 2 * self.max_tensors + 32, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize()
         dist.barrier(group=group)
 

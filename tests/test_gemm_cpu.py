@@ -125,3 +125,20 @@ def test_quantizer_module_forward_and_backward_casts():
     ident = Quantizer()
     z = torch.randn(5, requires_grad=True)
     assert torch.equal(ident(z), z)
+
+
+def test_tile_model_split_k_is_an_ordered_fold_of_the_splits():
+    """splits=1 is the unsplit model; splits=S partitions the K-slices into S contiguous ranges, accumulates each from
+    zero and folds the S results in order with a cast after every add."""
+    from cpd_b200 import float_quantize
+    torch.manual_seed(0)
+    a, b = torch.randn(5, 512), torch.randn(512, 7)
+    one = native.gemm_tile_cpu(a, b, 5, 2, rounding="ieee", k_slice=64, splits=1)
+    assert torch.equal(one, native.gemm_tile_cpu(a, b, 5, 2, rounding="ieee", k_slice=64))
+    four = native.gemm_tile_cpu(a, b, 5, 2, rounding="ieee", k_slice=64, splits=4)
+    parts = [native.gemm_tile_cpu(a[:, z * 128:(z + 1) * 128].contiguous(), b[z * 128:(z + 1) * 128].contiguous(), 5, 2,
+                                  rounding="ieee", k_slice=64) for z in range(4)]
+    acc = torch.zeros_like(parts[0])
+    for p in parts:
+        acc = float_quantize(acc + p, 5, 2, "ieee")
+    assert torch.equal(four, acc)

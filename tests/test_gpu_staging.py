@@ -77,6 +77,21 @@ def test_strided_padded_operands_and_split_k_match_matmul():
     assert (c.double() - ref).abs().max() <= 0.02 * ref.abs().max()
 
 
+@pytest.mark.parametrize("e,m,kahan", [(5, 10, False), (4, 3, False), (5, 2, True), (6, 9, False)])
+@pytest.mark.parametrize("splits", [3, 8])
+def test_split_k_is_the_ordered_quantised_fold_bit_for_bit(e, m, kahan, splits):
+    """Exact-sum operands (multiples of 1/8): the kernel's split-K result must equal the C++ CPU model of the same
+    partition (whole K-slices per split, splits folded in order with a cast after every add) bit for bit."""
+    torch.manual_seed(splits + e)
+    M, N, K = 96, 200, 4096
+    a = (torch.randint(-4, 5, (M, K), device="cuda").float() / 8)
+    b = (torch.randint(-4, 5, (N, K), device="cuda").float() / 8)
+    ao, bo = native.stage_matrix(a, native.OPERAND_BF16), native.stage_matrix(b, native.OPERAND_BF16)
+    got = native.gemm_tc(ao, bo, e, m, kahan, 128, native.OPERAND_BF16, None, k=K, splits=splits, variant=native.GEMM_1CTA).cpu()
+    want = native.gemm_tile_cpu(a.cpu(), b.cpu().t(), e, m, rounding="ieee", kahan=kahan, k_slice=128, splits=splits)
+    assert bool(((got == want) | (got.isnan() & want.isnan())).all()), float((got != want).float().mean())
+
+
 @pytest.mark.parametrize("chan_last", [False, True])
 @pytest.mark.parametrize("cfg", [(16, 32, 3, 1, 1), (32, 64, 3, 2, 1), (16, 24, 1, 2, 0), (3, 64, 3, 1, 1)])
 def test_tile_conv_forward_backward_match_conv2d(chan_last, cfg):
