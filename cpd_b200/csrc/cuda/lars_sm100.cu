@@ -21,7 +21,7 @@ namespace cpd {
 constexpr int kLarsThreads = 256;
 constexpr int kVec = 4;              // float4 vectors per thread per chunk (4 x 256 x 4 = 4096 elements)
 
-__global__ void __launch_bounds__(kLarsThreads, 3)
+__global__ void __launch_bounds__(kLarsThreads, 2)
 lars_kernel(float* master, float* model, const float* __restrict__ grad, float* mom,
             const Chunk* __restrict__ chunks, const int* __restrict__ tchunk_off, int n_chunks, int T,
             const float* __restrict__ lr_dev, float lr_host, float momentum, float wd, float coeff,
@@ -31,6 +31,11 @@ lars_kernel(float* master, float* model, const float* __restrict__ grad, float* 
   __shared__ float s_local_lr;
   const float lr = lr_dev ? *lr_dev : lr_host;
 
+  // LARS reads w and g twice (norms, then update).  Phase B therefore walks this CTA's chunks in REVERSE order - what
+  // phase A touched last is what L2 still holds - and the very last chunk of phase A never leaves the registers.
+  const int c_last = n_chunks <= (int)blockIdx.x ? -1
+                                                 : (int)blockIdx.x + ((n_chunks - 1 - (int)blockIdx.x) / (int)gridDim.x) * (int)gridDim.x;
+  float4 w_keep[kVec], g_keep[kVec];
   if (use_lars) {
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
       const Chunk ck = chunks[c];
@@ -51,6 +56,10 @@ lars_kernel(float* master, float* model, const float* __restrict__ grad, float* 
           w2 += w[k].x * w[k].x + w[k].y * w[k].y + w[k].z * w[k].z + w[k].w * w[k].w;
           g2 += g[k].x * g[k].x + g[k].y * g[k].y + g[k].z * g[k].z + g[k].w * g[k].w;
         }
+        if (c == c_last) {
+#pragma unroll
+          for (int k = 0; k < kVec; ++k) { w_keep[k] = w[k]; g_keep[k] = g[k]; }
+        }
       }
       w2 = block_sum_f32(w2, red);
       g2 = block_sum_f32(g2, red);
@@ -59,7 +68,7 @@ lars_kernel(float* master, float* model, const float* __restrict__ grad, float* 
     grid_barrier(bar);
   }
 
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+  for (int c = c_last; c >= 0; c -= gridDim.x) {
     const Chunk ck = chunks[c];
     const float wdt = wd * (wd_mult ? wd_mult[ck.tensor] : 1.f);
     float local_lr = 1.f;
@@ -91,7 +100,11 @@ lars_kernel(float* master, float* model, const float* __restrict__ grad, float* 
 #pragma unroll
       for (int k = 0; k < kVec; ++k) {        // 12 x 16 B in flight per thread
         const int v = threadIdx.x + k * kLarsThreads;
-        if (v < nvec) { w4[k] = wb[v]; g4[k] = gb[v]; b4[k] = bb[v]; }
+        if (v < nvec) {
+          b4[k] = bb[v];
+          if (use_lars && c == c_last) { w4[k] = w_keep[k]; g4[k] = g_keep[k]; }
+          else { w4[k] = wb[v]; g4[k] = gb[v]; }
+        }
       }
 #pragma unroll
       for (int k = 0; k < kVec; ++k) {
@@ -127,7 +140,7 @@ void lars_step_cuda(float* master, float* model, const float* grad, float* mom, 
                     const float* wd_mult, float* partials, unsigned* barrier_ws, int max_ctas,
                     cudaStream_t st) {
   if (n_chunks <= 0) return;
-  int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1) * 3;
+  int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1) * 2;   // 2 co-resident CTAs per SM (launch bounds), 12 x 16 B in flight per thread
   if (grid > n_chunks) grid = n_chunks;
   lars_kernel<<<grid, kLarsThreads, 0, st>>>(master, model, grad, mom, chunks, tchunk_off, n_chunks, T,
                                               lr_dev, lr, momentum, wd, coeff, eps, use_lars, nesterov,

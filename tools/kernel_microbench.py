@@ -92,6 +92,28 @@ def main():
             a, b = torch.randn(n, n, device="cuda"), torch.randn(n, n, device="cuda")
             ms = time_ms(lambda: quant_gemm(a, b, man=3, exp=4, mode="exact"), iters=5, flush=False)
             res["gemm_exact"].append({"n": n, "ms": round(ms, 4), "GFLOPs": round(2 * n ** 3 / ms / 1e6, 1)})
+    # tensor-core tile mode end to end: fp32 operands in, fused gather+cast staging (one launch per operand) + GEMM,
+    # against the same GEMM on pre-staged operands (kernel only) and cuBLAS bf16 on the same box
+    res["gemm_tile_e2e"], res["operand_stage"] = [], []
+    for n in ([4096] if args.quick else [4096, 8192]):
+        a, b = torch.randn(n, n, device="cuda"), torch.randn(n, n, device="cuda")
+        ao, bo = native.stage_matrix(a, native.OPERAND_BF16), native.stage_matrix(b.t(), native.OPERAND_BF16)
+        out = torch.empty(n, n, device="cuda")
+        ms_k = time_ms(lambda: native.gemm_tc(ao, bo, 5, 10, False, 0, native.OPERAND_BF16, None, out=out, k=n), iters=6, flush=False)
+        ms_e = time_ms(lambda: quant_gemm(a, b, man=10, exp=5, mode="tile", operands="bf16", k_slice=0), iters=6, flush=False)
+        ab, bb = a.bfloat16(), b.bfloat16()
+        ms_c = time_ms(lambda: torch.matmul(ab, bb), iters=6, flush=False)
+        ms_s = time_ms(lambda: native.stage_matrix(a, native.OPERAND_BF16), iters=6)
+        ms_st = time_ms(lambda: native.stage_matrix(b.t(), native.OPERAND_BF16), iters=6)
+        fl = 2 * n ** 3
+        res["gemm_tile_e2e"].append({"n": n, "kernel_only_ms": round(ms_k, 4), "kernel_only_TFLOPs": round(fl / ms_k / 1e9, 1),
+                                     "e2e_fp32_in_ms": round(ms_e, 4), "e2e_TFLOPs": round(fl / ms_e / 1e9, 1),
+                                     "e2e_over_kernel_only": round(ms_k / ms_e, 3), "cublas_bf16_ms": round(ms_c, 4),
+                                     "cublas_bf16_TFLOPs": round(fl / ms_c / 1e9, 1)})
+        res["operand_stage"].append({"n": n, "row_major_ms": round(ms_s, 4), "row_major_GBps": round(6 * n * n / ms_s / 1e6, 1),
+                                     "transposed_ms": round(ms_st, 4), "transposed_GBps": round(6 * n * n / ms_st / 1e6, 1),
+                                     "frac_of_hbm_" + src: round(6 * n * n / ms_s / 1e6 / hbm, 3)})
+        del a, b, ao, bo, out, ab, bb
     print(json.dumps(res, indent=1))
 
 

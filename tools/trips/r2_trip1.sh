@@ -31,3 +31,6 @@ echo "== bench ours N=1"; timeout 300 python bench.py --steps 30 --warmup 5 > $O
 echo "== bench ours N=1 overlap"; timeout 300 python bench.py --steps 30 --warmup 5 --overlap > $OUT/bench_ours_overlap.json 2>> $OUT/bench_ours.err; echo "rc=$?"; cut -c1-300 $OUT/bench_ours_overlap.json
 echo "== staging tests"; timeout 600 python -m pytest tests/test_gpu_staging.py -q -m gpu > $OUT/pytest_staging.log 2>&1; echo "rc=$?"; tail -30 $OUT/pytest_staging.log
 echo "== full GPU suite"; timeout 1500 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "rc=$?"; tail -6 $OUT/pytest_gpu.log
+echo "== bench resnet18_quant ours"; timeout 300 python bench.py --model resnet18_quant --steps 10 --warmup 3 > $OUT/bench_quant_ours.json 2> $OUT/bench_quant_ours.err; echo "rc=$?"; cut -c1-500 $OUT/bench_quant_ours.json; tail -5 $OUT/bench_quant_ours.err
+echo "== bench resnet18_quant reference"; timeout 600 python bench.py --model resnet18_quant --impl reference --steps 5 --warmup 3 > $OUT/bench_quant_ref.json 2> $OUT/bench_quant_ref.err; echo "rc=$?"; cut -c1-400 $OUT/bench_quant_ref.json; tail -5 $OUT/bench_quant_ref.err
+echo "== microbench"; timeout 400 python tools/kernel_microbench.py > $OUT/microbench.json 2> $OUT/microbench.err; echo "rc=$?"; python -c "import json; d=json.load(open(\"$OUT/microbench.json\")); print({k: d[k] for k in (\"aps_fold\",\"lars\",\"gemm_tile_e2e\",\"operand_stage\")})"; tail -3 $OUT/microbench.err
