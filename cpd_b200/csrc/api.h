@@ -110,6 +110,9 @@ struct StageDesc {
 };
 // operand_mode as in gemm_tc_cuda (0 bf16, 1 fp32/tf32, 2 e4m3, 3 e5m2); dst rows have Kp elements (Kp % 8 == 0)
 int operand_stage_cuda(const StageDesc& d, void* dst, long long R, long long K, long long Kp, int operand_mode, cudaStream_t st);
+// both operands of a GEMM in ONE launch (n = 1 or 2)
+int operand_stage2_cuda(const StageDesc* descs, void* const* dsts, const long long* R, const long long* K, const long long* Kp,
+                        int n, int operand_mode, cudaStream_t st);
 // out[j] = Q(sum_i x[i*ld + j]) : the bias gradient of Quant_Linear / Quant_Conv
 void colsum_quantize_cuda(const float* x, long long rows, int cols, long long ld, float* out, int e, int m, int rounding,
                           cudaStream_t st);

@@ -9,6 +9,7 @@
 #include <pybind11/stl.h>
 
 #include <atomic>
+#include <cstring>
 #include <stdexcept>
 
 #include "api.h"
@@ -95,25 +96,37 @@ PYBIND11_MODULE(_C, m) {
      py::arg("kahan"), py::arg("k_slice"), py::arg("operand_mode"), py::arg("bias"), py::arg("variant"), py::arg("stream"),
      py::arg("lda") = 0, py::arg("ldb") = 0, py::arg("splits") = 1, py::arg("workspace") = (uptr)0);
 
-  // operand staging: fp32 -> tensor-core operand (gather / im2col + cast), see cuda/operand_stage_sm100.cu
-  m.def("stage_gather_cuda", [](uptr src, int64_t base, int rows_fast, int64_t s_row, int64_t s1, int64_t s2, int64_t s3, int n2, int n3,
-                                uptr dst, int64_t R, int64_t K, int64_t Kp, int operand_mode, uptr stream) {
+  // operand staging: fp32 -> tensor-core operand (gather / im2col + cast), see cuda/operand_stage_sm100.cu.
+  // Descriptors are built once (opaque bytes) and one launch stages one or BOTH operands of a GEMM.
+  m.def("stage_gather_desc", [](uptr src, int64_t base, int rows_fast, int64_t s_row, int64_t s1, int64_t s2, int64_t s3, int n2, int n3) {
     cpd::StageDesc d{};
     d.src = P<const float>(src); d.base = base; d.mode = 0; d.rows_fast = rows_fast;
     d.s_row = s_row; d.s1 = s1; d.s2 = s2; d.s3 = s3; d.n2 = n2 < 1 ? 1 : n2; d.n3 = n3 < 1 ? 1 : n3;
-    int rc = cpd::operand_stage_cuda(d, P<void>(dst), R, K, Kp, operand_mode, S(stream));
-    check_launch("operand_stage(gather)");
-    return rc;
+    return py::bytes(reinterpret_cast<const char*>(&d), sizeof(d));
   });
-  m.def("stage_im2col_cuda", [](uptr src, int64_t base, int rows_fast, int taps_are_rows, int C, int H, int W, int OH, int OW, int KH, int KW,
-                                int stride, int pad, int dil, int in_dil, int64_t sb, int64_t sh, int64_t sw, int64_t sc,
-                                uptr dst, int64_t R, int64_t K, int64_t Kp, int operand_mode, uptr stream) {
+  m.def("stage_im2col_desc", [](uptr src, int64_t base, int rows_fast, int taps_are_rows, int C, int H, int W, int OH, int OW, int KH, int KW,
+                                int stride, int pad, int dil, int in_dil, int64_t sb, int64_t sh, int64_t sw, int64_t sc) {
     cpd::StageDesc d{};
     d.src = P<const float>(src); d.base = base; d.mode = 1; d.rows_fast = rows_fast; d.taps_are_rows = taps_are_rows;
     d.C = C; d.H = H; d.W = W; d.OH = OH; d.OW = OW; d.KH = KH; d.KW = KW; d.stride = stride; d.pad = pad; d.dil = dil;
     d.in_dil = in_dil < 1 ? 1 : in_dil; d.sb = sb; d.sh = sh; d.sw = sw; d.sc = sc; d.n2 = d.n3 = 1;
-    int rc = cpd::operand_stage_cuda(d, P<void>(dst), R, K, Kp, operand_mode, S(stream));
-    check_launch("operand_stage(im2col)");
+    return py::bytes(reinterpret_cast<const char*>(&d), sizeof(d));
+  });
+  m.def("stage_launch", [](std::vector<std::string> descs, std::vector<uptr> dsts, std::vector<int64_t> R, std::vector<int64_t> K,
+                           std::vector<int64_t> Kp, int operand_mode, uptr stream) {
+    const size_t n = descs.size();
+    if (n < 1 || n > 2 || dsts.size() != n || R.size() != n || K.size() != n || Kp.size() != n)
+      throw std::invalid_argument("stage_launch: one or two operands");
+    cpd::StageDesc d[2];
+    void* out[2];
+    long long r[2], k[2], kp[2];
+    for (size_t i = 0; i < n; ++i) {
+      if (descs[i].size() != sizeof(cpd::StageDesc)) throw std::invalid_argument("stage_launch: bad descriptor");
+      std::memcpy(&d[i], descs[i].data(), sizeof(cpd::StageDesc));
+      out[i] = P<void>(dsts[i]); r[i] = R[i]; k[i] = K[i]; kp[i] = Kp[i];
+    }
+    int rc = cpd::operand_stage2_cuda(d, out, r, k, kp, (int)n, operand_mode, S(stream));
+    check_launch("operand_stage");
     return rc;
   });
   m.def("colsum_quantize_cuda", [](uptr x, int64_t rows, int cols, int64_t ld, uptr out, int e, int mb, int rounding, uptr stream) {

@@ -85,14 +85,30 @@ __device__ __forceinline__ void stage_store8(void* dst_row, int k, const float (
   }
 }
 
+// One launch stages BOTH operands of a GEMM: the tile index space is the concatenation of operand 0's and operand 1's
+// tiles (a GEMM then costs two launches in total: this one and the tensor-core kernel).
+struct StagePair {
+  StageDesc d[2];
+  void* dst[2];
+  long long R[2], K[2], Kp[2];
+  int n;
+};
+
 template <int OP>
 __global__ void __launch_bounds__(kStageThreads)
-operand_stage_kernel(const StageDesc d, void* __restrict__ dst, long long R, long long K, long long Kp) {
+operand_stage_kernel(const StagePair sp) {
   __shared__ float tile[kTile][kTile + 1];
   constexpr int ES = OP == 0 ? 2 : (OP == 1 ? 4 : 1);
-  const long long tiles_k = (Kp + kTile - 1) / kTile;
-  const long long n_tiles = ((R + kTile - 1) / kTile) * tiles_k;
-  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+  const long long tk0 = (sp.Kp[0] + kTile - 1) / kTile;
+  const long long nt0 = ((sp.R[0] + kTile - 1) / kTile) * tk0;
+  const long long tk1 = sp.n > 1 ? (sp.Kp[1] + kTile - 1) / kTile : 1;
+  const long long nt1 = sp.n > 1 ? ((sp.R[1] + kTile - 1) / kTile) * tk1 : 0;
+  for (long long tt = blockIdx.x; tt < nt0 + nt1; tt += gridDim.x) {
+    const int which = tt >= nt0 ? 1 : 0;
+    const StageDesc& d = sp.d[which];
+    void* dst = sp.dst[which];
+    const long long R = sp.R[which], K = sp.K[which], Kp = sp.Kp[which];
+    const long long t = which ? tt - nt0 : tt, tiles_k = which ? tk1 : tk0;
     const long long r0 = (t / tiles_k) * kTile, k0 = (t % tiles_k) * kTile;
     // load phase: the source-contiguous dimension runs across the threads of a warp
 #pragma unroll 4
@@ -143,20 +159,33 @@ colsum_quantize_kernel(const float* __restrict__ x, long long rows, int cols, lo
 
 }  // namespace
 
-int operand_stage_cuda(const StageDesc& d, void* dst, long long R, long long K, long long Kp, int operand_mode, cudaStream_t st) {
-  if (R <= 0 || K <= 0) return 0;
-  if (Kp < K || Kp % 8) return -1;                       // rows are written in 8-element vectors
-  const long long n_tiles = ((R + kTile - 1) / kTile) * ((Kp + kTile - 1) / kTile);
+int operand_stage2_cuda(const StageDesc* descs, void* const* dsts, const long long* R, const long long* K, const long long* Kp,
+                        int n, int operand_mode, cudaStream_t st) {
+  if (n < 1 || n > 2) return -3;
+  StagePair sp{};
+  sp.n = n;
+  long long n_tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    if (R[i] <= 0 || K[i] <= 0) return -4;
+    if (Kp[i] < K[i] || Kp[i] % 8) return -1;                       // rows are written in 8-element vectors
+    sp.d[i] = descs[i]; sp.dst[i] = dsts[i]; sp.R[i] = R[i]; sp.K[i] = K[i]; sp.Kp[i] = Kp[i];
+    n_tiles += ((R[i] + kTile - 1) / kTile) * ((Kp[i] + kTile - 1) / kTile);
+  }
   const long long cap = (long long)device_sm_count(-1) * 8;
   const int grid = (int)(n_tiles < cap ? n_tiles : cap);
   switch (operand_mode) {
-    case 0: operand_stage_kernel<0><<<grid, kStageThreads, 0, st>>>(d, dst, R, K, Kp); break;
-    case 1: operand_stage_kernel<1><<<grid, kStageThreads, 0, st>>>(d, dst, R, K, Kp); break;
-    case 2: operand_stage_kernel<2><<<grid, kStageThreads, 0, st>>>(d, dst, R, K, Kp); break;
-    case 3: operand_stage_kernel<3><<<grid, kStageThreads, 0, st>>>(d, dst, R, K, Kp); break;
+    case 0: operand_stage_kernel<0><<<grid, kStageThreads, 0, st>>>(sp); break;
+    case 1: operand_stage_kernel<1><<<grid, kStageThreads, 0, st>>>(sp); break;
+    case 2: operand_stage_kernel<2><<<grid, kStageThreads, 0, st>>>(sp); break;
+    case 3: operand_stage_kernel<3><<<grid, kStageThreads, 0, st>>>(sp); break;
     default: return -2;
   }
   return 0;
+}
+
+int operand_stage_cuda(const StageDesc& d, void* dst, long long R, long long K, long long Kp, int operand_mode, cudaStream_t st) {
+  if (R <= 0 || K <= 0) return 0;
+  return operand_stage2_cuda(&d, &dst, &R, &K, &Kp, 1, operand_mode, st);
 }
 
 void colsum_quantize_cuda(const float* x, long long rows, int cols, long long ld, float* out, int e, int m, int rounding,

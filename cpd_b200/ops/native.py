@@ -189,43 +189,45 @@ def _staged_empty(R: int, K: int, operand_mode: int, device) -> torch.Tensor:
     return torch.empty(R, Kp, dtype=_OPERAND_TORCH[operand_mode], device=device)
 
 
-def stage_gather(src: torch.Tensor, R: int, sizes, strides, s_row: int, operand_mode: int, base: int = 0,
-                 rows_fast: Optional[bool] = None) -> torch.Tensor:
+class StageSpec:
+    """One operand of a tile-mode GEMM: an address-generator descriptor (gather or im2col) over an fp32 CUDA tensor,
+    its logical shape [R, K] and the output buffer.  ``stage(spec_a, spec_b)`` fills both in ONE launch."""
+
+    def __init__(self, src: torch.Tensor, desc: bytes, R: int, K: int, operand_mode: int):
+        self.src, self.desc, self.R, self.K, self.operand_mode = src, desc, int(R), int(K), int(operand_mode)
+        self.out = _staged_empty(self.R, self.K, operand_mode, src.device)
+
+
+def spec_gather(src: torch.Tensor, R: int, sizes, strides, s_row: int, operand_mode: int, base: int = 0,
+                rows_fast: Optional[bool] = None) -> StageSpec:
     """out[r, k] = src.flat[base + r * s_row + k1 * s1 + k2 * s2 + k3 * s3], k = (k1, k2, k3) row-major over ``sizes``,
-    cast to the operand dtype; returns [R, Kp] (use ``[:, :K]`` / pass ``k=K`` to gemm_tc).  Strides are in elements of
-    ``src``'s storage view and may be negative."""
+    cast to the operand dtype.  Strides are in elements of ``src``'s storage view and may be negative."""
     _f32(src, "src")
     if not src.is_cuda:
-        raise ValueError("stage_gather: CUDA tensor expected")
+        raise ValueError("stage: CUDA tensor expected")
     n1, n2, n3 = [int(v) for v in sizes]
     s1, s2, s3 = [int(v) for v in strides]
-    K = n1 * n2 * n3
     if rows_fast is None:
         rows_fast = abs(int(s_row)) == 1 and abs(s3) != 1
-    out = _staged_empty(R, K, operand_mode, src.device)
-    with torch.cuda.device(src.device):
-        rc = _C.stage_gather_cuda(src.data_ptr(), int(base), int(bool(rows_fast)), int(s_row), s1, s2, s3, n2, n3,
-                                  out.data_ptr(), R, K, out.shape[1], int(operand_mode), _stream(src))
-    if rc != 0:
-        raise RuntimeError(f"stage_gather: rejected (code {rc})")
-    return out
+    desc = _C.stage_gather_desc(src.data_ptr(), int(base), int(bool(rows_fast)), int(s_row), s1, s2, s3, n2, n3)
+    return StageSpec(src, desc, R, n1 * n2 * n3, operand_mode)
 
 
-def stage_matrix(x: torch.Tensor, operand_mode: int) -> torch.Tensor:
-    """Any 2-D fp32 view (transposed, sliced, ...) -> K-major operand [R, Kp]: no materialised transpose, no pad."""
+def spec_matrix(x: torch.Tensor, operand_mode: int) -> StageSpec:
+    """Any 2-D fp32 view (transposed, sliced, ...) as a K-major operand: no materialised transpose, no pad."""
     if x.dim() != 2:
-        raise ValueError("stage_matrix: 2-D tensor expected")
-    return stage_gather(x, x.shape[0], (1, 1, x.shape[1]), (0, 0, x.stride(1)), x.stride(0), operand_mode)
+        raise ValueError("stage: 2-D tensor expected")
+    return spec_gather(x, x.shape[0], (1, 1, x.shape[1]), (0, 0, x.stride(1)), x.stride(0), operand_mode)
 
 
-def stage_im2col(x: torch.Tensor, kh: int, kw: int, out_hw, stride: int, pad: int, dil: int, operand_mode: int,
-                 in_dil: int = 1, taps_are_rows: bool = False) -> torch.Tensor:
+def spec_im2col(x: torch.Tensor, kh: int, kw: int, out_hw, stride: int, pad: int, dil: int, operand_mode: int,
+                in_dil: int = 1, taps_are_rows: bool = False) -> StageSpec:
     """im2col of x[B, C, H, W] (any strides: NCHW or channels_last) fused with the operand cast:
     rows = output pixels (b, oh, ow), k = taps (kh, kw, c)  [taps_are_rows: the transposed matrix].  ``in_dil`` > 1
     treats x as zero-upsampled by that factor (data-gradient of a strided convolution)."""
     _f32(x, "x")
     if not x.is_cuda or x.dim() != 4:
-        raise ValueError("stage_im2col: 4-D CUDA tensor expected")
+        raise ValueError("stage: 4-D CUDA tensor expected")
     B, C, H, W = x.shape
     OH, OW = int(out_hw[0]), int(out_hw[1])
     pixels, taps = B * OH * OW, kh * kw * C
@@ -235,14 +237,34 @@ def stage_im2col(x: torch.Tensor, kh: int, kw: int, out_hw, stride: int, pad: in
     # fastest PIXEL index.  The kernel reads that dimension across the threads of a warp.
     chan_fast = sc == 1 and C > 1
     rows_fast = chan_fast == bool(taps_are_rows)
-    out = _staged_empty(R, K, operand_mode, x.device)
-    with torch.cuda.device(x.device):
-        rc = _C.stage_im2col_cuda(x.data_ptr(), 0, int(rows_fast), int(bool(taps_are_rows)), C, H, W, OH, OW, int(kh), int(kw),
-                                  int(stride), int(pad), int(dil), int(in_dil), sb, sh, sw, sc,
-                                  out.data_ptr(), R, K, out.shape[1], int(operand_mode), _stream(x))
+    desc = _C.stage_im2col_desc(x.data_ptr(), 0, int(rows_fast), int(bool(taps_are_rows)), C, H, W, OH, OW, int(kh), int(kw),
+                                int(stride), int(pad), int(dil), int(in_dil), sb, sh, sw, sc)
+    return StageSpec(x, desc, R, K, operand_mode)
+
+
+def stage(*specs: StageSpec):
+    """Fill the operand buffers of one or two specs with ONE kernel launch; returns the staged tensors ([R, Kp] each)."""
+    if not 1 <= len(specs) <= 2 or len({s.operand_mode for s in specs}) != 1:
+        raise ValueError("stage: one or two specs of the same operand type")
+    dev = specs[0].src.device
+    with torch.cuda.device(dev):
+        rc = _C.stage_launch([s.desc for s in specs], [s.out.data_ptr() for s in specs], [s.R for s in specs], [s.K for s in specs],
+                             [s.out.shape[1] for s in specs], specs[0].operand_mode, _stream(specs[0].src))
     if rc != 0:
-        raise RuntimeError(f"stage_im2col: rejected (code {rc})")
-    return out
+        raise RuntimeError(f"stage: rejected (code {rc})")
+    return tuple(s.out for s in specs) if len(specs) > 1 else specs[0].out
+
+
+def stage_gather(src, R, sizes, strides, s_row, operand_mode, base=0, rows_fast=None) -> torch.Tensor:
+    return stage(spec_gather(src, R, sizes, strides, s_row, operand_mode, base, rows_fast))
+
+
+def stage_matrix(x: torch.Tensor, operand_mode: int) -> torch.Tensor:
+    return stage(spec_matrix(x, operand_mode))
+
+
+def stage_im2col(x, kh, kw, out_hw, stride, pad, dil, operand_mode, in_dil=1, taps_are_rows=False) -> torch.Tensor:
+    return stage(spec_im2col(x, kh, kw, out_hw, stride, pad, dil, operand_mode, in_dil, taps_are_rows))
 
 
 def colsum_quantize(x2d: torch.Tensor, exp: int, man: int, rounding=ROUND_REF) -> torch.Tensor:

@@ -118,13 +118,13 @@ def splits_for(M: int, N: int, K: int, k_slice: int) -> int:
 def tile_gemm(a_view: torch.Tensor, bt_view: torch.Tensor, exp: int, man: int, kahan: bool = False, k_slice: int = 128,
               operands: Optional[str] = None, bias: Optional[torch.Tensor] = None, splits: Optional[int] = None) -> torch.Tensor:
     """C = a_view @ bt_view^T for two fp32 2-D VIEWS of any strides, on the tensor cores: each operand goes through ONE
-    staging launch (strided gather + cast to the operand type, K-major), the K tail is zero-filled by the TMA
-    descriptor, the bias is added in the GEMM epilogue.  No pad / .to() / .contiguous() / transposed copies."""
+    fused staging launch for BOTH operands (strided gather + cast to the operand type, K-major) and one tensor-core
+    launch: the K tail is zero-filled by the TMA descriptor, the bias is added in the GEMM epilogue.  No pad / .to() /
+    .contiguous() / transposed copies."""
     om = operand_mode_for(exp, man, operands)
     M, K = a_view.shape
     N = bt_view.shape[0]
-    a_op = native.stage_matrix(a_view, om)
-    b_op = native.stage_matrix(bt_view, om)
+    a_op, b_op = native.stage(native.spec_matrix(a_view, om), native.spec_matrix(bt_view, om))       # ONE launch, both operands
     if splits is None:
         splits = splits_for(M, N, K, k_slice)
     return native.gemm_tc(a_op, b_op, exp, man, bool(kahan), k_slice, om, bias, k=K, splits=splits)

@@ -80,8 +80,9 @@ class Quant_ConvTileFunction(Function):
       wgrad     dW[o, (kh,kw,c)]  = dy^T[o, (b,oh,ow)]  .  im2col(x)^T[(kh,kw,c), (b,oh,ow)]^T   (split-K + ordered fold)
 
     every operand is produced by ONE fused gather/im2col+cast launch from the fp32 tensor in whatever layout it has
-    (NCHW or channels_last), the outputs are channels_last views of the GEMM results (no permute copies).  4 launches
-    forward (2 staging + GEMM; bias fused), backward 3 + 4 (+1 bias gradient)."""
+    (NCHW or channels_last), both operands of a GEMM in the same launch; the outputs are channels_last views of the
+    GEMM results (no permute copies).  Launches: forward 2 (staging + GEMM, bias fused), backward 2 + 3 (split-K fold)
+    (+1 bias gradient) - against ~25 torch/extension launches per layer in the reference."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, exp, man, stride, padding, dilation, k_slice, operands, kahan):
@@ -90,9 +91,9 @@ class Quant_ConvTileFunction(Function):
         OH = (H + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
         OW = (W + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
         om = operand_mode_for(exp, man, operands)
-        a = native.stage_im2col(x, KH, KW, (OH, OW), stride, padding, dilation, om)
         ws = weight.stride()
-        bt = native.stage_gather(weight, O, (KH, KW, C), (ws[2], ws[3], ws[1]), ws[0], om)
+        a, bt = native.stage(native.spec_im2col(x, KH, KW, (OH, OW), stride, padding, dilation, om),
+                             native.spec_gather(weight, O, (KH, KW, C), (ws[2], ws[3], ws[1]), ws[0], om))
         K = KH * KW * C
         y = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, bias, k=K)                      # [B*OH*OW, O] == NHWC
         ctx.save_for_backward(x, weight)
@@ -109,16 +110,16 @@ class Quant_ConvTileFunction(Function):
         ws = weight.stride()
         if ctx.needs_input_grad[0]:
             pad_t = dilation * (KH - 1) - padding
-            a = native.stage_im2col(dy, KH, KW, (H, W), 1, pad_t, dilation, om, in_dil=stride)          # [(b,h,w), (kh,kw,o)]
             base = (KH - 1) * ws[2] + (KW - 1) * ws[3]
-            bt = native.stage_gather(weight, C, (KH, KW, O), (-ws[2], -ws[3], ws[0]), ws[1], om, base=base)   # flipped filter
+            a, bt = native.stage(native.spec_im2col(dy, KH, KW, (H, W), 1, pad_t, dilation, om, in_dil=stride),        # [(b,h,w), (kh,kw,o)]
+                                 native.spec_gather(weight, C, (KH, KW, O), (-ws[2], -ws[3], ws[0]), ws[1], om, base=base))   # flipped filter
             g = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, None, k=KH * KW * O)             # [(b,h,w), c] == NHWC
             dx = g.view(B, H, W, C).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
             ds = dy.stride()
             Mred = B * OH * OW
-            a = native.stage_gather(dy, O, (B, OH, OW), (ds[0], ds[2], ds[3]), ds[1], om)               # dy^T  [o, (b,oh,ow)]
-            bt = native.stage_im2col(x, KH, KW, (OH, OW), stride, padding, dilation, om, taps_are_rows=True)   # [(kh,kw,c), pixels]
+            a, bt = native.stage(native.spec_gather(dy, O, (B, OH, OW), (ds[0], ds[2], ds[3]), ds[1], om),        # dy^T  [o, (b,oh,ow)]
+                                 native.spec_im2col(x, KH, KW, (OH, OW), stride, padding, dilation, om, taps_are_rows=True))   # [(kh,kw,c), pixels]
             K = KH * KW * C
             g = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, None, k=Mred, splits=splits_for(O, K, Mred, k_slice))
             dw = g.view(O, KH, KW, C).permute(0, 3, 1, 2)
