@@ -135,3 +135,24 @@ def test_overlapped_bucketed_reduce_equals_sequential():
         assert bad < 1e-3, (graph, bad, float((w_ovl - w_seq).abs().max()))
         assert np.allclose(l_ovl, l_seq, rtol=1e-3), (graph, l_ovl, l_seq)
         assert l_seq[-1] < l_seq[0]
+
+
+def test_pipelined_input_prefetch_equals_plain_steps_on_gpu():
+    """prefetch / train_step_pipelined (pinned H2D of step i+1 on a copy stream behind the compute of step i, graph-captured
+    step) == the same batches through train_step: same losses, same weights."""
+    from cpd_b200.train import TrainEngine
+
+    def make():
+        torch.manual_seed(0)
+        m = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 8 * 8, 128), torch.nn.ReLU(), torch.nn.Linear(128, 10))
+        return TrainEngine(m, PrecisionConfig(grad_exp=5, grad_man=2, use_aps=True), batch_size=32, input_shape=(3, 8, 8), lr=0.05,
+                           cuda_graph=True, warmup_steps=1, channels_last=False)
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.randn(32, 3, 8, 8, generator=g).pin_memory(), torch.randint(0, 10, (32,), generator=g).pin_memory()) for _ in range(7)]
+    a, b = make(), make()
+    plain = [a.train_step(x, y) for (x, y) in batches]
+    b.prefetch(*batches[0])
+    piped = [b.train_step_pipelined(*(batches[i + 1] if i + 1 < len(batches) else (None, None))) for i in range(len(batches))]
+    torch.cuda.synchronize()
+    assert plain == piped, (plain, piped)
+    assert torch.equal(a.arena.model_flat, b.arena.model_flat)
