@@ -34,3 +34,9 @@ echo "== full GPU suite"; timeout 1500 python -m pytest tests -q -m gpu > $OUT/p
 echo "== bench resnet18_quant ours"; timeout 300 python bench.py --model resnet18_quant --steps 10 --warmup 3 > $OUT/bench_quant_ours.json 2> $OUT/bench_quant_ours.err; echo "rc=$?"; cut -c1-500 $OUT/bench_quant_ours.json; tail -5 $OUT/bench_quant_ours.err
 echo "== bench resnet18_quant reference"; timeout 600 python bench.py --model resnet18_quant --impl reference --steps 5 --warmup 3 > $OUT/bench_quant_ref.json 2> $OUT/bench_quant_ref.err; echo "rc=$?"; cut -c1-400 $OUT/bench_quant_ref.json; tail -5 $OUT/bench_quant_ref.err
 echo "== microbench"; timeout 400 python tools/kernel_microbench.py > $OUT/microbench.json 2> $OUT/microbench.err; echo "rc=$?"; python -c "import json; d=json.load(open(\"$OUT/microbench.json\")); print({k: d[k] for k in (\"aps_fold\",\"lars\",\"gemm_tile_e2e\",\"operand_stage\")})"; tail -3 $OUT/microbench.err
+echo "== trainer logs (kept under profiles/trainers/)"
+mkdir -p $OUT/trainers
+timeout 300 python examples/ResNet18/mix.py --grad_exp 4 --grad_man 3 --use_APS --max-iter 40 --dataset_len 8192 --val-len 1024 --val_freq 20 --print_freq 10 --workers 2 --save_path $OUT/trainers/r18 > $OUT/trainers/resnet18_mix.log 2>&1; echo "mix rc=$?"; tail -4 $OUT/trainers/resnet18_mix.log | cut -c1-200
+timeout 300 python examples/DavidNet/dawn.py --dist 0 --epoch 2 --dataset_len 8192 --grad_exp 5 --grad_man 2 --use_APS --use_kahan --use_lars --warm_up_epoch 1 > $OUT/trainers/davidnet_dawn.log 2>&1; echo "dawn rc=$?"; tail -5 $OUT/trainers/davidnet_dawn.log | cut -c1-200
+timeout 400 python examples/ResNet50/main.py --grad_exp 5 --grad_man 2 --use-APS --max-iter 20 --dataset-len 640 --val-len 64 --epochs 1 --workers 2 --log-dir $OUT/trainers/r50_logs --checkpoint-format $OUT/trainers/r50_ck/checkpoint-{epoch}.pth.tar > $OUT/trainers/resnet50_main.log 2>&1; echo "main rc=$?"; tail -4 $OUT/trainers/resnet50_main.log | cut -c1-200
+rm -rf $OUT/trainers/r18/*.pth $OUT/trainers/r50_ck
