@@ -61,5 +61,16 @@ if which in ("all", "fold", "lars"):
         for _ in range(3):
             native.lars_step(master, model, g, mom, tab.seg_off, 0.1, 0.9, 1e-4, use_lars=True, chunks=tab.chunks, tchunk_off=tab.tchunk_off,
                              lr_dev=lr, partials=partials, barrier_ws=bar)
+if which in ("stage", "conv"):
+    from cpd_b200 import Quant_Conv
+    x = torch.randn(64, 64, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    conv = Quant_Conv(64, 64, 3, padding=1, bias=False, exp=5, man=10, mode="tile", operands="bf16").cuda().to(memory_format=torch.channels_last)
+    for _ in range(3):                      # layer-1 shape of ResNet-18/CIFAR at batch 64: staging (im2col, transposed im2col), GEMMs, split-K fold
+        y = conv(x)
+        y.backward(torch.ones_like(y))
+if which in ("allreduce_fake",):
+    # the cross-GPU kernel told world = 8 with every peer aliased to this GPU (tools/fake_world.py): ncu can replay it
+    import subprocess
+    sys.exit(subprocess.call([sys.executable, os.path.join(ROOT, "tools", "fake_world.py"), "--max-bytes", str(1 << 26)]))
 torch.cuda.synchronize()
 print("done", which)

@@ -113,37 +113,47 @@ def sweep_md(js, out_md):
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:  # noqa: BLE001
         hbm = 6650.0
+    extra = []
     for r in rows:
         n = r["elems"]
-        best = min(v for k, v in r.items() if k.startswith("fused_") and k.endswith("_us") and "kahan" not in k and "phases" not in k)
+        best = min(v for k, v in r.items() if k.startswith("fused_") and k.endswith("_us") and "kahan" not in k and "phases" not in k
+                   and "fp32_auto" not in k and "nvls_fast" not in k)          # bit-exact low-bit variants only
         link_us = (2 * (W - 1) / W * n * 1) / (NVLINK_MEASURED_GBS * 1e3)          # two-shot wire bytes per GPU per direction
         hbm_us = (13.0 * n) / (hbm * 1e3)
         roof = max(link_us, hbm_us)
         bw = max(v for k, v in r.items() if k.startswith("fused_") and k.endswith("busbw_fp32_GBps"))
+        extra.append((r["fp32_bytes"], r.get("fused_fp32_auto_us"), r.get("fused_nvls_fast_us"), r.get("nccl_fp32_allreduce_us")))
         lines.append(f"| {r['fp32_bytes']} | {min(r.get('fused_oneshot_us', 1e9), r.get('fused_raw_us', 1e9)) if ('fused_oneshot_us' in r or 'fused_raw_us' in r) else '-'} | {r.get('fused_twoshot_us', '-')} | {r.get('fused_nvls_us', '-')} | {r.get('fused_auto_kahan_us', '-')} | "
                      f"{r.get('nccl_fp32_allreduce_us', '-')} | {r.get('reference_algo_us', '-')} | {bw} | {r.get('nccl_fp32_busbw_GBps', '-')} | {r.get('reference_algo_busbw_fp32_GBps', '-')} | "
                      f"{roof:.2f} | {roof / best:.3f} |")
+    if any(e[1] is not None for e in extra):
+        lines += ["", "In-switch modes: plain fp32 sum of the (8,23) path (`multimem.ld_reduce.add.f32`, reference = NCCL all_reduce) and the opt-in,",
+                  "NOT bit-exact fp8 in-switch sum (`algo=\"nvls_fast\"`, fp16 accumulator inside the NVSwitch).", "",
+                  "| fp32 bytes | fused fp32 (8,23) us | NCCL fp32 all_reduce us | nvls_fast (4,3)+APS us |", "|---|---|---|---|"]
+        lines += [f"| {b} | {f if f is not None else '-'} | {n if n is not None else '-'} | {q if q is not None else '-'} |" for (b, f, q, n) in extra]
     open(out_md, "w").write("\n".join(lines) + "\n")
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else "r2t*"        # which gpurun_out/ sub-directories (glob); round 1 used "trip*"
     os.makedirs(os.path.join(PR, "bench"), exist_ok=True)
     os.makedirs(os.path.join(PR, "ncu"), exist_ok=True)
-    for p in glob.glob(os.path.join(GO, "trip*", "bench*.json")):
+    for p in glob.glob(os.path.join(GO, only, "bench*.json")):
         if os.path.getsize(p) > 10:
             shutil.copy(p, os.path.join(PR, "bench", os.path.basename(os.path.dirname(p)) + "_" + os.path.basename(p)))
-    for p in glob.glob(os.path.join(GO, "trip*", "microbench.json")) + glob.glob(os.path.join(GO, "trip*", "bench_gemm.json")):
+    for p in glob.glob(os.path.join(GO, only, "microbench.json")) + glob.glob(os.path.join(GO, only, "bench_gemm.json")):
         if os.path.getsize(p) > 10:
             shutil.copy(p, os.path.join(PR, os.path.basename(os.path.dirname(p)) + "_" + os.path.basename(p)))
-    for p in glob.glob(os.path.join(GO, "trip*", "sweep.json")) + glob.glob(os.path.join(GO, "trip*", "check.json")) + \
-            glob.glob(os.path.join(GO, "trip*", "check_sweep.json")) + glob.glob(os.path.join(GO, "trip*", "fake8.json")):
+    for p in glob.glob(os.path.join(GO, only, "sweep.json")) + glob.glob(os.path.join(GO, only, "check.json")) + \
+            glob.glob(os.path.join(GO, only, "check_sweep.json")) + glob.glob(os.path.join(GO, only, "fake8.json")) + \
+            glob.glob(os.path.join(GO, only, "check_default.json")) + glob.glob(os.path.join(GO, only, "fake8_default.json")):
         tag = os.path.basename(os.path.dirname(p))
         shutil.copy(p, os.path.join(PR, f"allreduce_{tag}_{os.path.basename(p)}"))
-        if p.endswith("sweep.json"):
+        if p.endswith("sweep.json") or p.endswith("check_default.json"):
             sweep_md(p, os.path.join(PR, f"allreduce_{tag}_sweep.md"))
-    for p in glob.glob(os.path.join(GO, "trip*", "launches.csv")):
+    for p in glob.glob(os.path.join(GO, only, "launches.csv")) + glob.glob(os.path.join(GO, only, "launches_smoke.csv")):
         launch_summary(p, os.path.join(PR, f"launches_{os.path.basename(os.path.dirname(p))}.md"), "kernel launch list of one ResNet-18 training step (ours)")
-    for p in glob.glob(os.path.join(GO, "trip*", "*.ncu-rep")):
+    for p in glob.glob(os.path.join(GO, only, "*.ncu-rep")):
         tag = os.path.basename(os.path.dirname(p)) + "_" + os.path.basename(p).replace(".ncu-rep", "")
         ok = ncu_summary(p, os.path.join(PR, "ncu", tag + ".md"))
         print("ncu", tag, ok)
