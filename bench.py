@@ -149,7 +149,7 @@ def run_ours(args, cfg):
     eng = TrainEngine(model, pc, batch_size=cfg["batch"], input_shape=cfg["shape"], lr=cfg["lr"], momentum=0.9,
                       weight_decay=cfg["wd"], use_lars=cfg["use_lars"], nesterov=cfg["nesterov"], wd_mult=wd_mult,
                       loss_reduction=cfg["loss"], channels_last=not args.nchw, cuda_graph=not args.no_graph,
-                      fold_single=(args.model == "resnet50"))
+                      fold_single=(args.model == "resnet50"), steal_grads=args.steal_grads)
     stream = PinnedBatchStream(cfg["batch"] * pc.emulate_node, cfg["shape"], cfg["classes"], pool=4, seed=1234 + rank)
 
     # warm-up through the public API (also captures the CUDA graph)
@@ -202,7 +202,8 @@ def run_ours(args, cfg):
                             "nvls": bool(eng.reducer.symm.has_multicast) if eng.reducer.symm else False,
                             "wire_bits": eng.reducer.wire, "buckets": len(eng.reducer.buckets), "overlap": bool(pc.overlap),
                             "thresholds": eng.reducer.thresholds.to_dict(), "cuda_graph": not args.no_graph,
-                            "channels_last": not args.nchw, "e2e_input_pipelining": bool(args.pipelined)},
+                            "channels_last": not args.nchw, "e2e_input_pipelining": bool(args.pipelined),
+                            "steal_grads": bool(args.steal_grads)},
             "e2e": {"value": round(e2e, 1), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                     "h2d_bytes_per_step": stream.bytes_per_batch, "d2h_bytes_per_step": 8,
                     "note": "TrainEngine.train_step" + ("_pipelined" if args.pipelined else "") +
@@ -316,6 +317,8 @@ def main():
     ap.add_argument("--emulate-node", dest="emulate_node", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--nchw", action="store_true")
+    ap.add_argument("--steal-grads", dest="steal_grads", action="store_true",
+                    help="backward hands over fresh gradient tensors; one multi-tensor copy per bucket moves them into the arena")
     ap.add_argument("--pipelined", action="store_true", help="e2e loop through prefetch / train_step_pipelined (H2D overlapped)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

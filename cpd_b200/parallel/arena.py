@@ -155,6 +155,30 @@ class ModelArena:
             for p, g in zip(self.params, self.grad_views):
                 p.grad = g
 
+    def release_grads(self) -> None:
+        """``p.grad = None`` for every parameter: the next backward then HANDS autograd's freshly written gradient
+        tensors over instead of accumulating into the arena views (one read-modify-write kernel per parameter, plus the
+        arena memset); ``gather_grads`` moves them into the arena with multi-tensor copies."""
+        for p in self.params:
+            p.grad = None
+
+    def gather_grads(self, t0: int = 0, t1: Optional[int] = None) -> None:
+        """Copy the gradients of parameters [t0, t1) from wherever autograd put them into the arena (ONE multi-tensor
+        copy; parameters that received no gradient get zeros) and re-point ``p.grad`` at the arena views."""
+        t1 = len(self.params) if t1 is None else t1
+        src, dst = [], []
+        for t in range(t0, t1):
+            p, g = self.params[t], self.grad_views[t]
+            if p.grad is None:
+                g.zero_()
+            elif p.grad.data_ptr() != g.data_ptr():
+                src.append(p.grad)
+                dst.append(g)
+            p.grad = g
+        if src:
+            with torch.no_grad():
+                torch._foreach_copy_(dst, src)
+
     def table(self, t0: int = 0, t1: Optional[int] = None) -> ChunkTable:
         key = (t0, t1)
         if key not in self._tables:

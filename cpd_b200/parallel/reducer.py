@@ -187,6 +187,8 @@ class GradReducer:
             self._gather_buf = torch.empty(self.world, self.max_numel, dtype=torch.float32, device=self.device)
 
         self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory() if self.is_cuda else None
+        # set by TrainEngine(steal_grads=True): an overlapped bucket first moves its parameters' gradients into the arena
+        self.gather_before_launch = False
         # overlap machinery
         self._hooks = []
         self._pending = None
@@ -302,6 +304,9 @@ class GradReducer:
             self._armed = True
 
     def _launch_async(self, bi: int) -> None:
+        if self.gather_before_launch:
+            b = self.buckets[bi]
+            self.arena.gather_grads(b.t0, b.t1)            # on the compute stream, behind the kernels that wrote them
         cur = torch.cuda.current_stream(self.device)
         ev = torch.cuda.Event()
         ev.record(cur)

@@ -47,7 +47,8 @@ class TrainEngine:
                  nesterov: bool = False, wd_mult: Optional[Sequence[float]] = None, loss_reduction: str = "mean",
                  loss_scale: float = 1.0, channels_last: bool = True, cuda_graph: bool = True,
                  fold_single: bool = False, device: Optional[torch.device] = None, master_weights: bool = True,
-                 lars_eps: float = 0.0, warmup_steps: int = 3, amp_dtype: Optional[torch.dtype] = None):
+                 lars_eps: float = 0.0, warmup_steps: int = 3, amp_dtype: Optional[torch.dtype] = None,
+                 steal_grads: bool = False):
         self.cfg = cfg
         self.distributed = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size() if self.distributed else 1
@@ -57,6 +58,9 @@ class TrainEngine:
         self.device = device
         self.is_cuda = device.type == "cuda"
         self.E = int(cfg.emulate_node)
+        # steal_grads (E == 1): backward writes fresh gradient tensors (p.grad is None beforehand) and ONE multi-tensor copy
+        # per bucket moves them into the arena, instead of a memset + one accumulate kernel per parameter
+        self.steal_grads = bool(steal_grads) and self.E == 1
         self.batch_size = int(batch_size)
         self.loss_reduction, self.loss_scale = loss_reduction, float(loss_scale)
         # reduced-precision COMPUTE (the reference's dawn.py --half): autocast around forward + loss; parameters,
@@ -73,6 +77,7 @@ class TrainEngine:
         model._cpd_arena = self.arena
         self.emulate = EmulateNode(self.arena, cfg, fold_single=fold_single)
         self.reducer = GradReducer(self.arena, cfg)
+        self.reducer.gather_before_launch = bool(steal_grads) and self.E == 1
         self.optimizer = FusedSGD(self.arena, lr=lr, momentum=momentum, weight_decay=weight_decay, use_lars=use_lars,
                                   nesterov=nesterov, wd_mult=wd_mult, master_weights=master_weights, lars_eps=lars_eps)
 
@@ -107,9 +112,12 @@ class TrainEngine:
         nvtx = torch.cuda.nvtx if (self.is_cuda and _NVTX) else None
         self.loss_dev.zero_()
         denom = float(self.world * self.E)
-        overlap = self.cfg.overlap and self.E == 1
+        overlap = self.cfg.overlap and self.E == 1 and self.reducer._pending is not None      # hooks installed (CUDA)
         for k in range(self.E):
-            self.emulate.begin_micro(k)
+            if self.steal_grads:
+                self.arena.release_grads()
+            else:
+                self.emulate.begin_micro(k)
             if nvtx:
                 nvtx.range_push(f"fwd_bwd[{k}]")
             xin = self.x[k]
@@ -126,6 +134,8 @@ class TrainEngine:
                 nvtx.range_pop()
         if nvtx:
             nvtx.range_push("grad_sync")
+        if self.steal_grads and not overlap:
+            self.arena.gather_grads()
         self.emulate.fold()
         self.reducer.reduce()
         if nvtx:

@@ -97,3 +97,34 @@ def test_variant_selection_follows_the_measured_thresholds():
     assert r.algo_for(bucket(64)) == native.ALGO_ONESHOT                            # raw variant needs APS exponents
     r.cfg = PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, algo="twoshot")
     assert r.algo_for(bucket(64)) == native.ALGO_TWOSHOT
+
+
+def test_steal_grads_mode_equals_accumulate_into_arena_mode():
+    """TrainEngine(steal_grads=True): backward hands over fresh gradient tensors (p.grad None beforehand) and one
+    multi-tensor copy moves them into the arena - same losses and weights as accumulating into the arena views,
+    including a parameter that receives no gradient."""
+    from cpd_b200.train import TrainEngine
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Linear(48, 16)
+            self.unused = torch.nn.Linear(4, 4)                 # never in the graph: its gradient must read as zero
+            self.b = torch.nn.Linear(16, 10)
+
+        def forward(self, x):
+            return self.b(torch.relu(self.a(x.flatten(1))))
+
+    def run(steal):
+        torch.manual_seed(0)
+        eng = TrainEngine(Net(), PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True), batch_size=4, input_shape=(3, 4, 4), lr=0.05,
+                          weight_decay=1e-3, cuda_graph=False, steal_grads=steal)
+        g = torch.Generator().manual_seed(1)
+        x, y = torch.randn(4, 3, 4, 4, generator=g), torch.randint(0, 10, (4,), generator=g)
+        losses = [eng.train_step(x, y) for _ in range(4)]
+        assert all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(eng.arena.params, eng.arena.grad_views))
+        return losses, eng.arena.model_flat.clone()
+
+    l0, w0 = run(False)
+    l1, w1 = run(True)
+    assert l0 == l1 and torch.equal(w0, w1)

@@ -103,14 +103,15 @@ def test_overlapped_bucketed_reduce_equals_sequential():
     in a CUDA graph) give the same weights as reducing the same buckets after backward."""
     from cpd_b200.train import TrainEngine
 
-    def run(overlap, graph):
+    def run(overlap, graph, steal=False):
         torch.manual_seed(0)
         layers = []
         for _ in range(6):
             layers += [torch.nn.Linear(256, 256), torch.nn.ReLU()]
         m = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 8 * 8, 256), torch.nn.ReLU(), *layers, torch.nn.Linear(256, 10))
         eng = TrainEngine(m, PrecisionConfig(grad_exp=4, grad_man=3, use_aps=True, bucket_mb=0.3, overlap=overlap), batch_size=64,
-                          input_shape=(3, 8, 8), lr=0.05, use_lars=False, cuda_graph=graph, warmup_steps=1, channels_last=False)
+                          input_shape=(3, 8, 8), lr=0.05, use_lars=False, cuda_graph=graph, warmup_steps=1, channels_last=False,
+                          steal_grads=steal)
         assert len(eng.reducer.buckets) >= 4
         g = torch.Generator().manual_seed(1)
         x, y = torch.randn(64, 3, 8, 8, generator=g).pin_memory(), torch.randint(0, 10, (64,), generator=g).pin_memory()
@@ -135,6 +136,12 @@ def test_overlapped_bucketed_reduce_equals_sequential():
         assert bad < 1e-3, (graph, bad, float((w_ovl - w_seq).abs().max()))
         assert np.allclose(l_ovl, l_seq, rtol=1e-3), (graph, l_ovl, l_seq)
         assert l_seq[-1] < l_seq[0]
+        # steal_grads: fresh gradient tensors + one multi-tensor copy per bucket, with and without overlap
+        for ovl in (False, True):
+            w_st, l_st = run(ovl, graph, steal=True)
+            bad = ((w_st - w_seq).abs() > 3e-8 + 1e-6 * w_seq.abs()).float().mean().item()
+            assert bad < 1e-3, (graph, ovl, bad)
+            assert np.allclose(l_st, l_seq, rtol=1e-3), (graph, ovl, l_st, l_seq)
 
 
 def test_pipelined_input_prefetch_equals_plain_steps_on_gpu():
