@@ -144,6 +144,8 @@ def run_ours(args, cfg):
     pc = PrecisionConfig(grad_exp=cfg["grad_exp"], grad_man=cfg["grad_man"], use_aps=cfg["use_aps"], use_kahan=cfg["use_kahan"],
                          algo=args.algo, overlap=args.overlap, bucket_mb=args.bucket_mb, emulate_node=args.emulate_node)
     model_kw = dict(exp=cfg["gemm_exp"], man=cfg["gemm_man"], mode="tile", operands="bf16") if "gemm_exp" in cfg else {}
+    if args.fused_bn and args.model != "davidnet":
+        model_kw["fused_bn"] = True              # BatchNorm + shortcut add + ReLU in this repo's kernels (same arithmetic)
     model = create_model(cfg["arch"], **model_kw)
     wd_mult = bn_bias_no_decay(model.named_parameters()) if args.model == "resnet50" else None
     eng = TrainEngine(model, pc, batch_size=cfg["batch"], input_shape=cfg["shape"], lr=cfg["lr"], momentum=0.9,
@@ -203,7 +205,7 @@ def run_ours(args, cfg):
                             "wire_bits": eng.reducer.wire, "buckets": len(eng.reducer.buckets), "overlap": bool(pc.overlap),
                             "thresholds": eng.reducer.thresholds.to_dict(), "cuda_graph": not args.no_graph,
                             "channels_last": not args.nchw, "e2e_input_pipelining": bool(args.pipelined),
-                            "steal_grads": bool(args.steal_grads)},
+                            "steal_grads": bool(args.steal_grads), "fused_bn": bool(args.fused_bn)},
             "e2e": {"value": round(e2e, 1), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                     "h2d_bytes_per_step": stream.bytes_per_batch, "d2h_bytes_per_step": 8,
                     "note": "TrainEngine.train_step" + ("_pipelined" if args.pipelined else "") +
@@ -317,6 +319,8 @@ def main():
     ap.add_argument("--emulate-node", dest="emulate_node", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--nchw", action="store_true")
+    ap.add_argument("--fused-bn", dest="fused_bn", action="store_true",
+                    help="BatchNormAct2d: BatchNorm + shortcut add + ReLU fused (csrc/cuda/bn_act_sm100.cu) instead of cuDNN BN + ATen elementwise")
     ap.add_argument("--steal-grads", dest="steal_grads", action="store_true",
                     help="backward hands over fresh gradient tensors; one multi-tensor copy per bucket moves them into the arena")
     ap.add_argument("--pipelined", action="store_true", help="e2e loop through prefetch / train_step_pipelined (H2D overlapped)")

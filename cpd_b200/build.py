@@ -35,6 +35,7 @@ CUDA_SOURCES = [
     "cuda/gemm_tcgen05_mx_sm100a.cu",
     "cuda/mx_quantize_sm100.cu",
     "cuda/operand_stage_sm100.cu",
+    "cuda/bn_act_sm100.cu",
     "cuda/allreduce_fused_sm100a.cu",
 ]
 CPP_SOURCES = [

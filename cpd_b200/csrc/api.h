@@ -117,6 +117,16 @@ int operand_stage2_cuda(const StageDesc* descs, void* const* dsts, const long lo
 void colsum_quantize_cuda(const float* x, long long rows, int cols, long long ld, float* out, int e, int m, int rounding,
                           cudaStream_t st);
 
+// Training-mode BatchNorm2d fused with the residual add and ReLU that follow it (cuda/bn_act_sm100.cu), channels_last fp32:
+// x, res, y, dy, dx, dres are [M = N*H*W, C] row-major, C % 4 == 0.  stats = mean | rstd | scale | bias (4*C floats),
+// grads = dgamma | dbeta | c1 | c2 (4*C floats); workspace: bn_workspace_floats(M, C) floats, zero-initialised once.
+long long bn_workspace_floats(long long M, int C);
+int bn_act_forward_cuda(const float* x, const float* res, float* y, long long M, int C, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                        bool relu, float* stats, float* workspace, cudaStream_t st);
+int bn_act_backward_cuda(const float* dy, const float* y, const float* x, float* dx, float* dres, long long M, int C,
+                         const float* gamma, const float* stats, bool relu, float* grads, float* workspace, cudaStream_t st);
+
 // tcgen05 / TMEM / TMA GEMM with per-K-slice accumulator re-quantisation.
 // operand_mode: 0 = bf16 operands (kind::f16), 1 = tf32 (kind::tf32), 2 = e4m3, 3 = e5m2
 // variant: 0 = auto, 1 = 128x128 single-CTA tiles, 2 = 256x256 CTA-pair tiles (cta_group::2 cluster kernel,

@@ -1,0 +1,327 @@
+// bn_act_sm100.cu — training-mode BatchNorm2d fused with the residual add and the ReLU that follow it, channels_last fp32.
+//
+// The benchmark networks of the reference (example/ResNet18/models/resnet18_cifar.py:10-45, torchvision's ResNet-50,
+// example/DavidNet/davidnet.py) are conv -> BatchNorm -> (+ shortcut) -> ReLU chains.  Run through stock modules that is
+// a cuDNN BN kernel, an elementwise add and a clamp forward, and a threshold kernel plus a cuDNN BN-backward kernel
+// backward: 13-16 full passes over the activation tensor per BN layer, 42 % of a ResNet-18/CIFAR step on a B200
+// (profiles/launches_trip1.md: batchnorm 24 %, elementwise 18 %).  These kernels do the same arithmetic in 10-12 passes
+// and 4 launches per layer:
+//   bn_stats_kernel      per-channel sum / sum of squares of (x - shift)          (shift = running mean: the shifted-data
+//                        formula keeps fp32 sums accurate when |mean| >> std); the LAST CTA of a channel tile reduces
+//                        the per-CTA partials in a fixed order (deterministic) and writes mean, rstd, the folded
+//                        scale / bias of the apply pass and the running statistics
+//   bn_apply_kernel      y = relu(x * scale + bias (+ residual))
+//   bn_bwd_stats_kernel  dz = dy * [y > 0];  per-channel sum dz, sum dz * xhat;  last CTA: dgamma, dbeta, coefficients
+//   bn_bwd_apply_kernel  dx = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat))   (+ dz as the shortcut's gradient)
+// x is [M = N*H*W, C] row-major (NHWC), C % 4 == 0; a warp reads 16-byte vectors along C, rows are strided over the block.
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../api.h"
+#include "../common/device_utils.cuh"
+
+namespace cpd {
+
+namespace {
+
+constexpr int kBnThreads = 256;
+
+struct BnGeom {
+  int lanes;          // threads along channels (each owns 4 channels): min(C / 4, 32)
+  int rows_par;       // rows processed in parallel by a block: 256 / lanes
+  int ctiles;         // channel tiles of lanes * 4 channels
+  int slabs;          // row slabs (grid.y)
+  long long rows_per_slab;
+};
+
+inline BnGeom bn_geom(long long M, int C, int sms) {
+  BnGeom g;
+  g.lanes = C / 4 < 32 ? C / 4 : 32;
+  g.rows_par = kBnThreads / g.lanes;
+  g.ctiles = (C / 4 + g.lanes - 1) / g.lanes;
+  long long want = (long long)sms * 4 / g.ctiles;
+  if (want < 1) want = 1;
+  long long max_slabs = (M + g.rows_par * 8 - 1) / (g.rows_par * 8);       // at least 8 rows per thread
+  if (max_slabs < 1) max_slabs = 1;
+  g.slabs = (int)(want < max_slabs ? want : max_slabs);
+  g.rows_per_slab = (M + g.slabs - 1) / g.slabs;
+  return g;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// block-level reduction of two float4 accumulators over the rows_par dimension; result valid for ty == 0
+__device__ __forceinline__ void reduce_rows(float4& a, float4& b, int lanes, int rows_par, float4* sm) {
+  const int lane = threadIdx.x % lanes, ty = threadIdx.x / lanes;
+  sm[threadIdx.x] = a;
+  sm[kBnThreads + threadIdx.x] = b;
+  __syncthreads();
+  if (ty == 0) {
+    for (int r = 1; r < rows_par; ++r) {
+      const float4 u = sm[r * lanes + lane], v = sm[kBnThreads + r * lanes + lane];
+      a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+      b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+    }
+  }
+  __syncthreads();
+}
+
+// ---- forward: statistics ------------------------------------------------------------------------------------------
+// part: [slabs][2][C]; stats out: mean[C], rstd[C], scale[C] = gamma * rstd, bias[C] = beta - mean * scale
+__global__ void __launch_bounds__(kBnThreads)
+bn_stats_kernel(const float* __restrict__ x, long long M, int C, long long rows_per_slab, int lanes,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ running_mean,
+                float* __restrict__ running_var, float momentum, float eps, float* __restrict__ part,
+                unsigned* __restrict__ counters, float* __restrict__ mean, float* __restrict__ rstd,
+                float* __restrict__ scale, float* __restrict__ bias, long long* __restrict__ num_batches_tracked) {
+  __shared__ float4 sm[2 * kBnThreads];
+  __shared__ bool last;
+  const int rows_par = kBnThreads / lanes;
+  const int lane = threadIdx.x % lanes, ty = threadIdx.x / lanes;
+  const int c0 = (blockIdx.x * lanes + lane) * 4;
+  const bool cok = c0 < C;
+  const float4 sh = cok ? ld4(running_mean + c0) : make_float4(0.f, 0.f, 0.f, 0.f);       // shift of the shifted-data sums
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  const long long r0 = (long long)blockIdx.y * rows_per_slab;
+  const long long r1 = r0 + rows_per_slab < M ? r0 + rows_per_slab : M;
+  if (cok) {
+    long long r = r0 + ty;
+    for (; r + 3LL * rows_par < r1; r += 4LL * rows_par) {            // 4 independent 16-byte loads in flight
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = ld4(x + (r + (long long)j * rows_par) * C + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = v[j].x - sh.x, b = v[j].y - sh.y, c = v[j].z - sh.z, d = v[j].w - sh.w;
+        s.x += a; s.y += b; s.z += c; s.w += d;
+        q.x += a * a; q.y += b * b; q.z += c * c; q.w += d * d;
+      }
+    }
+    for (; r < r1; r += rows_par) {
+      const float4 v = ld4(x + r * C + c0);
+      const float a = v.x - sh.x, b = v.y - sh.y, c = v.z - sh.z, d = v.w - sh.w;
+      s.x += a; s.y += b; s.z += c; s.w += d;
+      q.x += a * a; q.y += b * b; q.z += c * c; q.w += d * d;
+    }
+  }
+  reduce_rows(s, q, lanes, rows_par, sm);
+  if (ty == 0 && cok) {
+    *reinterpret_cast<float4*>(part + ((long long)blockIdx.y * 2 + 0) * C + c0) = s;
+    *reinterpret_cast<float4*>(part + ((long long)blockIdx.y * 2 + 1) * C + c0) = q;
+  }
+  // last CTA of this channel tile: fixed-order reduction of the slab partials
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&counters[blockIdx.x], 1u);
+    last = done == gridDim.y - 1;
+    if (last) counters[blockIdx.x] = 0u;                        // ready for the next launch / graph replay
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;     // nn.BatchNorm2d's counter
+  const int nch = lanes * 4;
+  for (int i = threadIdx.x; i < nch; i += kBnThreads) {
+    const int c = blockIdx.x * nch + i;
+    if (c >= C) continue;
+    double ds = 0.0, dq = 0.0;
+    for (int sl = 0; sl < (int)gridDim.y; ++sl) {
+      ds += (double)__ldcg(&part[((long long)sl * 2 + 0) * C + c]);       // written by other SMs: read at L2
+      dq += (double)__ldcg(&part[((long long)sl * 2 + 1) * C + c]);
+    }
+    const double shift = (double)running_mean[c];
+    const double ms = ds / (double)M;                             // mean of (x - shift)
+    double var = dq / (double)M - ms * ms;                        // biased variance
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)(ms + shift);
+    const float rs = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * rs;
+    mean[c] = mu; rstd[c] = rs; scale[c] = sc; bias[c] = beta[c] - mu * sc;
+    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// ---- forward: apply -----------------------------------------------------------------------------------------------
+template <bool RELU, bool RES>
+__global__ void __launch_bounds__(kBnThreads)
+bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ y, long long n4, int C4,
+                const float* __restrict__ scale, const float* __restrict__ bias) {
+  const long long stride = (long long)gridDim.x * kBnThreads;
+  for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < n4; i += stride) {
+    const int c0 = (int)(i % C4) * 4;
+    const float4 v = ld4(x + i * 4), sc = ld4(scale + c0), bi = ld4(bias + c0);
+    float4 o = make_float4(v.x * sc.x + bi.x, v.y * sc.y + bi.y, v.z * sc.z + bi.z, v.w * sc.w + bi.w);
+    if (RES) {
+      const float4 r = ld4(res + i * 4);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    *reinterpret_cast<float4*>(y + i * 4) = o;
+  }
+}
+
+// ---- backward: statistics -----------------------------------------------------------------------------------------
+// coef out: c1[C] = mean(dz), c2[C] = mean(dz * xhat); dgamma[C], dbeta[C]
+template <bool RELU>
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, long long M, int C,
+                    long long rows_per_slab, int lanes, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    float* __restrict__ part, unsigned* __restrict__ counters, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2) {
+  __shared__ float4 sm[2 * kBnThreads];
+  __shared__ bool last;
+  const int rows_par = kBnThreads / lanes;
+  const int lane = threadIdx.x % lanes, ty = threadIdx.x / lanes;
+  const int c0 = (blockIdx.x * lanes + lane) * 4;
+  const bool cok = c0 < C;
+  const float4 mu = cok ? ld4(mean + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 rs = cok ? ld4(rstd + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  const long long r0 = (long long)blockIdx.y * rows_per_slab;
+  const long long r1 = r0 + rows_per_slab < M ? r0 + rows_per_slab : M;
+  if (cok) {
+    for (long long r = r0 + ty; r < r1; r += 2LL * rows_par) {
+      const bool two = r + rows_par < r1;
+      const long long ra = r * C + c0, rb = (r + rows_par) * C + c0;
+      float4 g0 = ld4(dy + ra), x0 = ld4(x + ra), g1, x1, y0, y1;
+      if (RELU) y0 = ld4(y + ra);
+      if (two) { g1 = ld4(dy + rb); x1 = ld4(x + rb); if (RELU) y1 = ld4(y + rb); }
+      if (RELU) {
+        g0.x = y0.x > 0.f ? g0.x : 0.f; g0.y = y0.y > 0.f ? g0.y : 0.f; g0.z = y0.z > 0.f ? g0.z : 0.f; g0.w = y0.w > 0.f ? g0.w : 0.f;
+      }
+      s.x += g0.x; s.y += g0.y; s.z += g0.z; s.w += g0.w;
+      q.x += g0.x * (x0.x - mu.x) * rs.x; q.y += g0.y * (x0.y - mu.y) * rs.y;
+      q.z += g0.z * (x0.z - mu.z) * rs.z; q.w += g0.w * (x0.w - mu.w) * rs.w;
+      if (two) {
+        if (RELU) {
+          g1.x = y1.x > 0.f ? g1.x : 0.f; g1.y = y1.y > 0.f ? g1.y : 0.f; g1.z = y1.z > 0.f ? g1.z : 0.f; g1.w = y1.w > 0.f ? g1.w : 0.f;
+        }
+        s.x += g1.x; s.y += g1.y; s.z += g1.z; s.w += g1.w;
+        q.x += g1.x * (x1.x - mu.x) * rs.x; q.y += g1.y * (x1.y - mu.y) * rs.y;
+        q.z += g1.z * (x1.z - mu.z) * rs.z; q.w += g1.w * (x1.w - mu.w) * rs.w;
+      }
+    }
+  }
+  reduce_rows(s, q, lanes, rows_par, sm);
+  if (ty == 0 && cok) {
+    *reinterpret_cast<float4*>(part + ((long long)blockIdx.y * 2 + 0) * C + c0) = s;
+    *reinterpret_cast<float4*>(part + ((long long)blockIdx.y * 2 + 1) * C + c0) = q;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&counters[blockIdx.x], 1u);
+    last = done == gridDim.y - 1;
+    if (last) counters[blockIdx.x] = 0u;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const int nch = lanes * 4;
+  for (int i = threadIdx.x; i < nch; i += kBnThreads) {
+    const int c = blockIdx.x * nch + i;
+    if (c >= C) continue;
+    double ds = 0.0, dq = 0.0;
+    for (int sl = 0; sl < (int)gridDim.y; ++sl) {
+      ds += (double)__ldcg(&part[((long long)sl * 2 + 0) * C + c]);       // written by other SMs: read at L2
+      dq += (double)__ldcg(&part[((long long)sl * 2 + 1) * C + c]);
+    }
+    dbeta[c] = (float)ds;
+    dgamma[c] = (float)dq;
+    c1[c] = (float)(ds / (double)M);
+    c2[c] = (float)(dq / (double)M);
+  }
+}
+
+// ---- backward: apply ----------------------------------------------------------------------------------------------
+template <bool RELU, bool RES>
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, float* __restrict__ dx,
+                    float* __restrict__ dres, long long n4, int C4, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ gamma, const float* __restrict__ c1, const float* __restrict__ c2) {
+  const long long stride = (long long)gridDim.x * kBnThreads;
+  for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < n4; i += stride) {
+    const int c0 = (int)(i % C4) * 4;
+    float4 g = ld4(dy + i * 4);
+    const float4 v = ld4(x + i * 4);
+    if (RELU) {
+      const float4 o = ld4(y + i * 4);
+      g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+    }
+    if (RES) *reinterpret_cast<float4*>(dres + i * 4) = g;
+    const float4 mu = ld4(mean + c0), rs = ld4(rstd + c0), ga = ld4(gamma + c0), a = ld4(c1 + c0), b = ld4(c2 + c0);
+    float4 o;
+    o.x = ga.x * rs.x * (g.x - a.x - (v.x - mu.x) * rs.x * b.x);
+    o.y = ga.y * rs.y * (g.y - a.y - (v.y - mu.y) * rs.y * b.y);
+    o.z = ga.z * rs.z * (g.z - a.z - (v.z - mu.z) * rs.z * b.z);
+    o.w = ga.w * rs.w * (g.w - a.w - (v.w - mu.w) * rs.w * b.w);
+    *reinterpret_cast<float4*>(dx + i * 4) = o;
+  }
+}
+
+int ew_grid(long long n4, int sms) {
+  long long b = (n4 + kBnThreads - 1) / kBnThreads;
+  const long long cap = (long long)sms * 8;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+// workspace: float part[slabs_max * 2 * C] + unsigned counters[ctiles]; stats: float[4 * C] = mean | rstd | scale | bias
+long long bn_workspace_floats(long long M, int C) {
+  const BnGeom g = bn_geom(M, C, device_sm_count(-1));
+  return (long long)g.slabs * 2 * C + g.ctiles + 8;
+}
+
+int bn_act_forward_cuda(const float* x, const float* res, float* y, long long M, int C, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                        bool relu, float* stats, float* workspace, cudaStream_t st) {
+  if (M <= 0 || C <= 0) return 0;
+  if (C % 4) return -1;
+  const int sms = device_sm_count(-1);
+  const BnGeom g = bn_geom(M, C, sms);
+  float* part = workspace;
+  unsigned* counters = reinterpret_cast<unsigned*>(workspace + (long long)g.slabs * 2 * C);
+  float *mean = stats, *rstd = stats + C, *scale = stats + 2 * C, *bias = stats + 3 * C;
+  bn_stats_kernel<<<dim3(g.ctiles, g.slabs), kBnThreads, 0, st>>>(x, M, C, g.rows_per_slab, g.lanes, gamma, beta, running_mean, running_var,
+                                                                   momentum, eps, part, counters, mean, rstd, scale, bias,
+                                                                   num_batches_tracked);
+  const long long n4 = M * C / 4;
+  const int grid = ew_grid(n4, sms);
+  if (relu && res) bn_apply_kernel<true, true><<<grid, kBnThreads, 0, st>>>(x, res, y, n4, C / 4, scale, bias);
+  else if (relu) bn_apply_kernel<true, false><<<grid, kBnThreads, 0, st>>>(x, res, y, n4, C / 4, scale, bias);
+  else if (res) bn_apply_kernel<false, true><<<grid, kBnThreads, 0, st>>>(x, res, y, n4, C / 4, scale, bias);
+  else bn_apply_kernel<false, false><<<grid, kBnThreads, 0, st>>>(x, res, y, n4, C / 4, scale, bias);
+  return 0;
+}
+
+// grads: float[4 * C] = dgamma | dbeta | c1 | c2
+int bn_act_backward_cuda(const float* dy, const float* y, const float* x, float* dx, float* dres, long long M, int C,
+                         const float* gamma, const float* stats, bool relu, float* grads, float* workspace, cudaStream_t st) {
+  if (M <= 0 || C <= 0) return 0;
+  if (C % 4) return -1;
+  const int sms = device_sm_count(-1);
+  const BnGeom g = bn_geom(M, C, sms);
+  float* part = workspace;
+  unsigned* counters = reinterpret_cast<unsigned*>(workspace + (long long)g.slabs * 2 * C);
+  const float *mean = stats, *rstd = stats + C;
+  float *dgamma = grads, *dbeta = grads + C, *c1 = grads + 2 * C, *c2 = grads + 3 * C;
+  if (relu)
+    bn_bwd_stats_kernel<true><<<dim3(g.ctiles, g.slabs), kBnThreads, 0, st>>>(dy, y, x, M, C, g.rows_per_slab, g.lanes, mean, rstd, part,
+                                                                                counters, dgamma, dbeta, c1, c2);
+  else
+    bn_bwd_stats_kernel<false><<<dim3(g.ctiles, g.slabs), kBnThreads, 0, st>>>(dy, y, x, M, C, g.rows_per_slab, g.lanes, mean, rstd, part,
+                                                                                 counters, dgamma, dbeta, c1, c2);
+  const long long n4 = M * C / 4;
+  const int grid = ew_grid(n4, sms);
+  if (relu && dres) bn_bwd_apply_kernel<true, true><<<grid, kBnThreads, 0, st>>>(dy, y, x, dx, dres, n4, C / 4, mean, rstd, gamma, c1, c2);
+  else if (relu) bn_bwd_apply_kernel<true, false><<<grid, kBnThreads, 0, st>>>(dy, y, x, dx, dres, n4, C / 4, mean, rstd, gamma, c1, c2);
+  else if (dres) bn_bwd_apply_kernel<false, true><<<grid, kBnThreads, 0, st>>>(dy, y, x, dx, dres, n4, C / 4, mean, rstd, gamma, c1, c2);
+  else bn_bwd_apply_kernel<false, false><<<grid, kBnThreads, 0, st>>>(dy, y, x, dx, dres, n4, C / 4, mean, rstd, gamma, c1, c2);
+  return 0;
+}
+
+}  // namespace cpd

@@ -8,24 +8,34 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+def _bn(c, fused, relu):
+    if fused:
+        from ..nn import BatchNormAct2d
+        return BatchNormAct2d(c, relu=relu)
+    return nn.BatchNorm2d(c)
+
+
 class Bottleneck(nn.Module):
     expansion = 4
 
-    def __init__(self, cin, width, stride=1):
+    def __init__(self, cin, width, stride=1, fused_bn=False):
         super().__init__()
         cout = width * self.expansion
+        self.fused_bn = fused_bn
         self.conv1 = nn.Conv2d(cin, width, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(width)
+        self.bn1 = _bn(width, fused_bn, True)
         self.conv2 = nn.Conv2d(width, width, 3, stride=stride, padding=1, bias=False)
-        self.bn2 = nn.BatchNorm2d(width)
+        self.bn2 = _bn(width, fused_bn, True)
         self.conv3 = nn.Conv2d(width, cout, 1, bias=False)
-        self.bn3 = nn.BatchNorm2d(cout)
+        self.bn3 = _bn(cout, fused_bn, True)
         self.downsample = None
         if stride != 1 or cin != cout:
-            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False), nn.BatchNorm2d(cout))
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False), _bn(cout, fused_bn, False))
 
     def forward(self, x):
         idt = x if self.downsample is None else self.downsample(x)
+        if self.fused_bn:                                        # BN+ReLU, BN+ReLU, BN+shortcut+ReLU: 4 launches each
+            return self.bn3(self.conv3(self.bn2(self.conv2(self.bn1(self.conv1(x))))), idt)
         y = F.relu(self.bn1(self.conv1(x)), inplace=True)
         y = F.relu(self.bn2(self.conv2(y)), inplace=True)
         y = self.bn3(self.conv3(y))
@@ -35,18 +45,21 @@ class Bottleneck(nn.Module):
 class Basic(nn.Module):
     expansion = 1
 
-    def __init__(self, cin, width, stride=1):
+    def __init__(self, cin, width, stride=1, fused_bn=False):
         super().__init__()
+        self.fused_bn = fused_bn
         self.conv1 = nn.Conv2d(cin, width, 3, stride=stride, padding=1, bias=False)
-        self.bn1 = nn.BatchNorm2d(width)
+        self.bn1 = _bn(width, fused_bn, True)
         self.conv2 = nn.Conv2d(width, width, 3, padding=1, bias=False)
-        self.bn2 = nn.BatchNorm2d(width)
+        self.bn2 = _bn(width, fused_bn, True)
         self.downsample = None
         if stride != 1 or cin != width:
-            self.downsample = nn.Sequential(nn.Conv2d(cin, width, 1, stride=stride, bias=False), nn.BatchNorm2d(width))
+            self.downsample = nn.Sequential(nn.Conv2d(cin, width, 1, stride=stride, bias=False), _bn(width, fused_bn, False))
 
     def forward(self, x):
         idt = x if self.downsample is None else self.downsample(x)
+        if self.fused_bn:
+            return self.bn2(self.conv2(self.bn1(self.conv1(x))), idt)
         y = F.relu(self.bn1(self.conv1(x)), inplace=True)
         y = self.bn2(self.conv2(y))
         return F.relu(y + idt, inplace=True)
@@ -54,16 +67,17 @@ class Basic(nn.Module):
 
 class ResNet(nn.Module):
     """ImageNet ResNet-18/34/50/101 with torchvision's parameter layout (the reference uses torchvision.models.resnet50)."""
-    def __init__(self, block, layers, num_classes=1000):
+    def __init__(self, block, layers, num_classes=1000, fused_bn=False):
         super().__init__()
+        self.fused_bn = fused_bn
         self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
-        self.bn1 = nn.BatchNorm2d(64)
+        self.bn1 = _bn(64, fused_bn, True)
         self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
         cin, stages = 64, []
         for i, n in enumerate(layers):
             width = 64 * 2 ** i
             for j in range(n):
-                stages.append(block(cin, width, stride=(2 if (i > 0 and j == 0) else 1)))
+                stages.append(block(cin, width, stride=(2 if (i > 0 and j == 0) else 1), fused_bn=fused_bn))
                 cin = width * block.expansion
         self.layers = nn.Sequential(*stages)
         self.fc = nn.Linear(cin, num_classes)
@@ -75,23 +89,23 @@ class ResNet(nn.Module):
                 nn.init.zeros_(m.bias)
 
     def forward(self, x, rank=None):
-        x = self.maxpool(F.relu(self.bn1(self.conv1(x)), inplace=True))
+        x = self.maxpool(self.bn1(self.conv1(x)) if self.fused_bn else F.relu(self.bn1(self.conv1(x)), inplace=True))
         x = self.layers(x)
         x = F.adaptive_avg_pool2d(x, 1).flatten(1)
         return self.fc(x)
 
 
-def resnet18(num_classes=1000):
-    return ResNet(Basic, (2, 2, 2, 2), num_classes)
+def resnet18(num_classes=1000, fused_bn=False):
+    return ResNet(Basic, (2, 2, 2, 2), num_classes, fused_bn=fused_bn)
 
 
-def resnet34(num_classes=1000):
-    return ResNet(Basic, (3, 4, 6, 3), num_classes)
+def resnet34(num_classes=1000, fused_bn=False):
+    return ResNet(Basic, (3, 4, 6, 3), num_classes, fused_bn=fused_bn)
 
 
-def resnet50(num_classes=1000):
-    return ResNet(Bottleneck, (3, 4, 6, 3), num_classes)
+def resnet50(num_classes=1000, fused_bn=False):
+    return ResNet(Bottleneck, (3, 4, 6, 3), num_classes, fused_bn=fused_bn)
 
 
-def resnet101(num_classes=1000):
-    return ResNet(Bottleneck, (3, 4, 23, 3), num_classes)
+def resnet101(num_classes=1000, fused_bn=False):
+    return ResNet(Bottleneck, (3, 4, 23, 3), num_classes, fused_bn=fused_bn)

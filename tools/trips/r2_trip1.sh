@@ -30,6 +30,9 @@ PY
 echo "== bench ours N=1"; timeout 300 python bench.py --steps 30 --warmup 5 > $OUT/bench_ours.json 2> $OUT/bench_ours.err; echo "rc=$?"; cut -c1-600 $OUT/bench_ours.json; tail -3 $OUT/bench_ours.err
 echo "== bench ours N=1 steal"; timeout 300 python bench.py --steps 30 --warmup 5 --steal-grads > $OUT/bench_ours_steal.json 2>> $OUT/bench_ours.err; echo "rc=$?"; cut -c1-200 $OUT/bench_ours_steal.json
 echo "== bench ours N=1 overlap+steal+pipelined"; timeout 300 python bench.py --steps 30 --warmup 5 --overlap --steal-grads --pipelined > $OUT/bench_ours_all.json 2>> $OUT/bench_ours.err; echo "rc=$?"; cut -c1-200 $OUT/bench_ours_all.json; python -c "import json; d=json.loads(open(\"$OUT/bench_ours_all.json\").read().strip().splitlines()[-1]); print(d[\"e2e\"])"
+echo "== fused BN tests"; timeout 400 python -m pytest tests/test_gpu_fused_bn.py -q -m gpu > $OUT/pytest_bn.log 2>&1; echo "rc=$?"; tail -12 $OUT/pytest_bn.log
+echo "== bench ours N=1 fused-bn"; timeout 300 python bench.py --steps 30 --warmup 5 --fused-bn > $OUT/bench_ours_fusedbn.json 2>> $OUT/bench_ours.err; echo "rc=$?"; cut -c1-200 $OUT/bench_ours_fusedbn.json
+echo "== bench ours N=1 fused-bn+steal+pipelined"; timeout 300 python bench.py --steps 30 --warmup 5 --fused-bn --steal-grads --pipelined > $OUT/bench_ours_fusedbn_all.json 2>> $OUT/bench_ours.err; echo "rc=$?"; cut -c1-200 $OUT/bench_ours_fusedbn_all.json
 echo "== bench ours N=1 overlap"; timeout 300 python bench.py --steps 30 --warmup 5 --overlap > $OUT/bench_ours_overlap.json 2>> $OUT/bench_ours.err; echo "rc=$?"; cut -c1-300 $OUT/bench_ours_overlap.json
 echo "== staging tests"; timeout 600 python -m pytest tests/test_gpu_staging.py -q -m gpu > $OUT/pytest_staging.log 2>&1; echo "rc=$?"; tail -30 $OUT/pytest_staging.log
 echo "== full GPU suite"; timeout 1500 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "rc=$?"; tail -6 $OUT/pytest_gpu.log
