@@ -144,7 +144,7 @@ def run_ours(args, cfg):
     pc = PrecisionConfig(grad_exp=cfg["grad_exp"], grad_man=cfg["grad_man"], use_aps=cfg["use_aps"], use_kahan=cfg["use_kahan"],
                          algo=args.algo, overlap=args.overlap, bucket_mb=args.bucket_mb, emulate_node=args.emulate_node)
     model_kw = dict(exp=cfg["gemm_exp"], man=cfg["gemm_man"], mode="tile", operands="bf16") if "gemm_exp" in cfg else {}
-    if args.fused_bn and args.model != "davidnet":
+    if args.fused_bn:
         model_kw["fused_bn"] = True              # BatchNorm + shortcut add + ReLU in this repo's kernels (same arithmetic)
     model = create_model(cfg["arch"], **model_kw)
     wd_mult = bn_bias_no_decay(model.named_parameters()) if args.model == "resnet50" else None

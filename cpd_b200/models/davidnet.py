@@ -63,10 +63,15 @@ class GraphNet(nn.Module):
         return outs[0] if len(outs) == 1 else dict(zip(self.out_names, outs))
 
 
-def _conv_bn(nodes, name, src, cin, cout, pool=False):
+def _conv_bn(nodes, name, src, cin, cout, pool=False, fused_bn=False):
     nodes.append((f"{name}_conv", nn.Conv2d(cin, cout, 3, padding=1, bias=False), [src]))
-    nodes.append((f"{name}_bn", nn.BatchNorm2d(cout), [f"{name}_conv"]))
-    nodes.append((f"{name}_relu", nn.ReLU(inplace=True), [f"{name}_bn"]))
+    if fused_bn:                                    # BatchNorm + ReLU in this repo's kernels; the relu node stays as a pass-through
+        from ..nn import BatchNormAct2d
+        nodes.append((f"{name}_bn", BatchNormAct2d(cout, relu=True), [f"{name}_conv"]))
+        nodes.append((f"{name}_relu", nn.Identity(), [f"{name}_bn"]))
+    else:
+        nodes.append((f"{name}_bn", nn.BatchNorm2d(cout), [f"{name}_conv"]))
+        nodes.append((f"{name}_relu", nn.ReLU(inplace=True), [f"{name}_bn"]))
     last = f"{name}_relu"
     if pool:
         nodes.append((f"{name}_pool", nn.MaxPool2d(2), [last]))
@@ -74,21 +79,21 @@ def _conv_bn(nodes, name, src, cin, cout, pool=False):
     return last
 
 
-def _residual(nodes, name, src, c):
-    a = _conv_bn(nodes, f"{name}_res1", src, c, c)
-    b = _conv_bn(nodes, f"{name}_res2", a, c, c)
+def _residual(nodes, name, src, c, fused_bn=False):
+    a = _conv_bn(nodes, f"{name}_res1", src, c, c, fused_bn=fused_bn)
+    b = _conv_bn(nodes, f"{name}_res2", a, c, c, fused_bn=fused_bn)
     nodes.append((f"{name}_add", Add(), [src, b]))
     return f"{name}_add"
 
 
 def davidnet(channels=(64, 128, 256, 512), num_classes: int = 10, logit_scale: float = 0.125,
-             res_layers=(1, 3)) -> GraphNet:
+             res_layers=(1, 3), fused_bn: bool = False) -> GraphNet:
     nodes: List = []
-    cur = _conv_bn(nodes, "prep", "input", 3, channels[0])
+    cur = _conv_bn(nodes, "prep", "input", 3, channels[0], fused_bn=fused_bn)
     for i in (1, 2, 3):
-        cur = _conv_bn(nodes, f"layer{i}", cur, channels[i - 1], channels[i], pool=True)
+        cur = _conv_bn(nodes, f"layer{i}", cur, channels[i - 1], channels[i], pool=True, fused_bn=fused_bn)
         if i in res_layers:
-            cur = _residual(nodes, f"layer{i}", cur, channels[i])
+            cur = _residual(nodes, f"layer{i}", cur, channels[i], fused_bn=fused_bn)
     nodes.append(("pool", nn.MaxPool2d(4), [cur]))
     nodes.append(("flatten", nn.Flatten(1), ["pool"]))
     nodes.append(("linear", nn.Linear(channels[3], num_classes, bias=False), ["flatten"]))
