@@ -41,6 +41,11 @@ CONFIGS = {
                            use_kahan=False, use_lars=False, nesterov=False, lr=0.1, wd=1e-4, loss="mean",
                            gemm_exp=5, gemm_man=10, label="ResNet-18/CIFAR-shape with Quant_Conv (5,10) GEMM accumulators"),
 }
+# Engine options of the "ours" arm and their defaults = what measured fastest on the B200 box (profiles/README.md);
+# every one has a --no-... switch.  They change HOW the step is executed, never WHAT it computes (same architecture,
+# fp32/TF32 compute, same batch, same gradient format).
+DEFAULT_FLAGS = dict(overlap=False, pipelined=False, fused_bn=False, steal_grads=False)
+
 # published reference numbers: only ResNet-50 has one (<= ~1068 img/s on 8xV100, derived bound)
 PUBLISHED = {"resnet50": 1068.0}
 
@@ -314,16 +319,17 @@ def main():
     ap.add_argument("--allreduce-sweep", dest="allreduce_sweep", action="store_true",
                     help="BASELINE config 5: all-reduce time / bus GB/s sweep instead of a training benchmark (needs --gpus >= 2)")
     ap.add_argument("--sweep-max-bytes", dest="sweep_max_bytes", type=int, default=1 << 30)
-    ap.add_argument("--overlap", action="store_true")
+    ap.add_argument("--overlap", action=argparse.BooleanOptionalAction, default=DEFAULT_FLAGS["overlap"],
+                    help="bucketed gradient reduction launched from autograd hooks on a comm stream, small comm grids")
     ap.add_argument("--bucket-mb", dest="bucket_mb", type=float, default=0.0)
     ap.add_argument("--emulate-node", dest="emulate_node", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--nchw", action="store_true")
-    ap.add_argument("--fused-bn", dest="fused_bn", action="store_true",
+    ap.add_argument("--fused-bn", dest="fused_bn", action=argparse.BooleanOptionalAction, default=DEFAULT_FLAGS["fused_bn"],
                     help="BatchNormAct2d: BatchNorm + shortcut add + ReLU fused (csrc/cuda/bn_act_sm100.cu) instead of cuDNN BN + ATen elementwise")
-    ap.add_argument("--steal-grads", dest="steal_grads", action="store_true",
+    ap.add_argument("--steal-grads", dest="steal_grads", action=argparse.BooleanOptionalAction, default=DEFAULT_FLAGS["steal_grads"],
                     help="backward hands over fresh gradient tensors; one multi-tensor copy per bucket moves them into the arena")
-    ap.add_argument("--pipelined", action="store_true", help="e2e loop through prefetch / train_step_pipelined (H2D overlapped)")
+    ap.add_argument("--pipelined", action=argparse.BooleanOptionalAction, default=DEFAULT_FLAGS["pipelined"], help="e2e loop through prefetch / train_step_pipelined (H2D overlapped)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus != world and world == 1 and args.gpus > 1:
