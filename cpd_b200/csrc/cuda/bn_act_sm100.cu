@@ -150,16 +150,29 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ y, long long n4, int C4,
                 const float* __restrict__ scale, const float* __restrict__ bias) {
   const long long stride = (long long)gridDim.x * kBnThreads;
-  for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < n4; i += stride) {
-    const int c0 = (int)(i % C4) * 4;
-    const float4 v = ld4(x + i * 4), sc = ld4(scale + c0), bi = ld4(bias + c0);
-    float4 o = make_float4(v.x * sc.x + bi.x, v.y * sc.y + bi.y, v.z * sc.z + bi.z, v.w * sc.w + bi.w);
-    if (RES) {
-      const float4 r = ld4(res + i * 4);
-      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+  // two independent vectors per thread per iteration: 32-64 B in flight per thread keeps HBM busy at 2048 threads / SM
+  for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < n4; i += 2 * stride) {
+    const long long j = i + stride;
+    const bool two = j < n4;
+    const float4 v0 = ld4(x + i * 4);
+    const float4 v1 = two ? ld4(x + j * 4) : v0;
+    float4 r0, r1;
+    if (RES) { r0 = ld4(res + i * 4); r1 = two ? ld4(res + j * 4) : r0; }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const long long e = h ? j : i;
+      const float4 v = h ? v1 : v0;
+      const int c0 = (int)(e % C4) * 4;
+      const float4 sc = ld4(scale + c0), bi = ld4(bias + c0);
+      float4 o = make_float4(v.x * sc.x + bi.x, v.y * sc.y + bi.y, v.z * sc.z + bi.z, v.w * sc.w + bi.w);
+      if (RES) {
+        const float4 r = h ? r1 : r0;
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      *reinterpret_cast<float4*>(y + e * 4) = o;
     }
-    if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    *reinterpret_cast<float4*>(y + i * 4) = o;
   }
 }
 
