@@ -217,7 +217,8 @@ def spec_matrix(x: torch.Tensor, operand_mode: int) -> StageSpec:
     """Any 2-D fp32 view (transposed, sliced, ...) as a K-major operand: no materialised transpose, no pad."""
     if x.dim() != 2:
         raise ValueError("stage: 2-D tensor expected")
-    return spec_gather(x, x.shape[0], (1, 1, x.shape[1]), (0, 0, x.stride(1)), x.stride(0), operand_mode)
+    return spec_gather(x, x.shape[0], (x.shape[1], 1, 1), (x.stride(1), 0, 0), x.stride(0), operand_mode,
+                       rows_fast=(abs(x.stride(0)) == 1 and abs(x.stride(1)) != 1))
 
 
 def spec_im2col(x: torch.Tensor, kh: int, kw: int, out_hw, stride: int, pad: int, dil: int, operand_mode: int,

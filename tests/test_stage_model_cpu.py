@@ -38,7 +38,7 @@ def _gather(src, R, sizes, strides, s_row, om, base=0, rows_fast=None):
 
 
 def _matrix(x, om):
-    return _gather(x, x.shape[0], (1, 1, x.shape[1]), (0, 0, x.stride(1)), x.stride(0), om)
+    return _gather(x, x.shape[0], (x.shape[1], 1, 1), (x.stride(1), 0, 0), x.stride(0), om)
 
 
 def _im2col(x, kh, kw, out_hw, stride, pad, dil, om, in_dil=1, taps_are_rows=False):
