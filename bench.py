@@ -147,7 +147,8 @@ def run_ours(args, cfg):
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(0)
     pc = PrecisionConfig(grad_exp=cfg["grad_exp"], grad_man=cfg["grad_man"], use_aps=cfg["use_aps"], use_kahan=cfg["use_kahan"],
-                         algo=args.algo, overlap=args.overlap, bucket_mb=args.bucket_mb, emulate_node=args.emulate_node)
+                         algo=args.algo, overlap=args.overlap, bucket_mb=args.bucket_mb, emulate_node=args.emulate_node,
+                         comm_ctas=args.comm_ctas)
     model_kw = dict(exp=cfg["gemm_exp"], man=cfg["gemm_man"], mode="tile", operands="bf16") if "gemm_exp" in cfg else {}
     if args.fused_bn:
         model_kw["fused_bn"] = True              # BatchNorm + shortcut add + ReLU in this repo's kernels (same arithmetic)
@@ -207,7 +208,7 @@ def run_ours(args, cfg):
             "dtype": DTYPE, "data": DATA, "impl": "ours", "config": config,
             "impl_detail": {"allreduce": eng.reducer.mode + (":" + (eng.reducer.symm.backend if eng.reducer.symm else "-")),
                             "nvls": bool(eng.reducer.symm.has_multicast) if eng.reducer.symm else False,
-                            "wire_bits": eng.reducer.wire, "buckets": len(eng.reducer.buckets), "overlap": bool(pc.overlap),
+                            "wire_bits": eng.reducer.wire, "buckets": len(eng.reducer.buckets), "overlap": bool(pc.overlap), "comm_ctas": int(pc.comm_ctas), "bucket_mb": float(pc.bucket_mb),
                             "thresholds": eng.reducer.thresholds.to_dict(), "cuda_graph": not args.no_graph,
                             "channels_last": not args.nchw, "e2e_input_pipelining": bool(args.pipelined),
                             "steal_grads": bool(args.steal_grads), "fused_bn": bool(args.fused_bn)},
@@ -322,6 +323,7 @@ def main():
     ap.add_argument("--overlap", action=argparse.BooleanOptionalAction, default=DEFAULT_FLAGS["overlap"],
                     help="bucketed gradient reduction launched from autograd hooks on a comm stream, small comm grids")
     ap.add_argument("--bucket-mb", dest="bucket_mb", type=float, default=0.0)
+    ap.add_argument("--comm-ctas", dest="comm_ctas", type=int, default=0, help="grid of an overlapped bucket's reduction (0: 32)")
     ap.add_argument("--emulate-node", dest="emulate_node", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--nchw", action="store_true")

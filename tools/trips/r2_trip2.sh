@@ -16,9 +16,9 @@ timeout 900 $TR --master-port $port tools/multigpu_check.py --specials --section
    --max-bytes $MAXB --out $OUT/check_default.json > $OUT/check_default.log 2>&1; echo "rc=$?"
 grep -E "^\[correct|^\[stress|^\[fault|^\[topo|FAIL|Error" $OUT/check_default.log | head -12 | cut -c1-400
 if [ "$MODE" = full ]; then
-for v in PACK_HW_OFF POLL_CTA0 WEAK_LOADS NO_EXTRA_FENCE; do
+for v in NO_EXTRA_FENCE WEAK_LOADS BOTH; do
   port=$((port + 1))
-  case $v in PACK_HW_OFF) E="CPD_B200_PACK_HW=0";; *) E="CPD_B200_$v=1";; esac
+  case $v in PACK_HW_OFF) E="CPD_B200_PACK_HW=0";; BOTH) E="CPD_B200_WEAK_LOADS=1 CPD_B200_NO_EXTRA_FENCE=1";; *) E="CPD_B200_$v=1";; esac
   echo "== variant $v: check + sweep to 64 MB"
   env $E timeout 420 $TR --master-port $port tools/multigpu_check.py --sections correct,sweep --max-bytes $((1<<26)) \
      --out $OUT/check_$v.json > $OUT/check_$v.log 2>&1; echo "rc=$?"
@@ -43,7 +43,7 @@ for f in sorted(glob.glob("$OUT/check_*.json")):
 PY
 echo "== calibration"; port=$((port + 1))
 timeout 200 $TR --master-port $port tools/calibrate_run.py > $OUT/calibrate.log 2>&1; echo "rc=$?"; grep -E "calibrate|thresholds" $OUT/calibrate.log | tail -8 | cut -c1-300
-for cfg in "resnet18:" "resnet18:--overlap" "resnet18:--overlap --pipelined" "davidnet:--overlap" "resnet50:--overlap" "resnet18_quant:"; do
+for cfg in "resnet18:" "resnet18:--pipelined" "resnet18:--overlap" "resnet18:--overlap --comm-ctas 148 --bucket-mb 24" "resnet18:--overlap --comm-ctas 74 --bucket-mb 24" "davidnet:" "resnet50:" "resnet18_quant:"; do
   m=${cfg%%:*}; fl=${cfg#*:}; tag=$(echo "$m$fl" | tr -d ' -')
   port=$((port + 1))
   echo "== bench ours $m $fl N=$N"
@@ -61,5 +61,7 @@ for m in resnet18 resnet18_quant; do
   timeout 600 $TR --master-port $port bench.py --gpus $N --steps 8 --warmup 3 --model $m --impl reference > $OUT/bench_ref_$m.json 2> $OUT/bench_ref_$m.err; echo "rc=$?"; cut -c1-250 $OUT/bench_ref_$m.json
 done
 fi
+if [ "${SWEEPBENCH:-0}" = 1 ]; then
 echo "== bench.py --allreduce-sweep"; port=$((port + 1))
 timeout 400 $TR --master-port $port bench.py --gpus $N --allreduce-sweep --sweep-max-bytes $((1<<28)) > $OUT/bench_sweep.json 2> $OUT/bench_sweep.err; echo "rc=$?"; cut -c1-300 $OUT/bench_sweep.json
+fi
