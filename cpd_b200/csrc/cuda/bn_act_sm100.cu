@@ -66,6 +66,39 @@ __device__ __forceinline__ void reduce_rows(float4& a, float4& b, int lanes, int
   __syncthreads();
 }
 
+// Last CTA of a channel tile: reduce the [slabs][2][C] partials of the tile's channels in a FIXED order, with the whole
+// block (a serial per-channel loop over ~600 slabs cost ~20 us of dependent L2 round trips per launch: 40 launches a
+// step).  Thread (lane, g) sums slabs g, g + G, g + 2G, ... of its 4 channels with independent vector loads; the G group
+// sums are then combined in group order.  Result: sum / sumsq per channel in shared memory (double).
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ part, int slabs, int C, int lanes, double* s_sum, double* s_sq,
+                                                double4* scratch) {
+  const int G = kBnThreads / lanes;
+  const int lane = threadIdx.x % lanes, g = threadIdx.x / lanes;
+  const int c0 = (blockIdx.x * lanes + lane) * 4;
+  double4 a = make_double4(0.0, 0.0, 0.0, 0.0), b = a;
+  if (c0 < C) {
+    for (int sl = g; sl < slabs; sl += G) {
+      const float4 u = __ldcg(reinterpret_cast<const float4*>(part + ((long long)sl * 2 + 0) * C + c0));     // other SMs wrote these
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + ((long long)sl * 2 + 1) * C + c0));
+      a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+      b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+    }
+  }
+  scratch[threadIdx.x] = a;
+  scratch[kBnThreads + threadIdx.x] = b;
+  __syncthreads();
+  if (g == 0 && c0 < C) {
+    for (int j = 1; j < G; ++j) {
+      const double4 u = scratch[j * lanes + lane], v = scratch[kBnThreads + j * lanes + lane];
+      a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+      b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+    }
+    s_sum[lane * 4 + 0] = a.x; s_sum[lane * 4 + 1] = a.y; s_sum[lane * 4 + 2] = a.z; s_sum[lane * 4 + 3] = a.w;
+    s_sq[lane * 4 + 0] = b.x; s_sq[lane * 4 + 1] = b.y; s_sq[lane * 4 + 2] = b.z; s_sq[lane * 4 + 3] = b.w;
+  }
+  __syncthreads();
+}
+
 // ---- forward: statistics ------------------------------------------------------------------------------------------
 // part: [slabs][2][C]; stats out: mean[C], rstd[C], scale[C] = gamma * rstd, bias[C] = beta - mean * scale
 __global__ void __launch_bounds__(kBnThreads)
@@ -121,15 +154,14 @@ bn_stats_kernel(const float* __restrict__ x, long long M, int C, long long rows_
   if (!last) return;
   __threadfence();
   if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;     // nn.BatchNorm2d's counter
+  __shared__ double s_sum[128], s_sq[128];
+  __shared__ double4 scratch[2 * kBnThreads];
+  reduce_partials(part, (int)gridDim.y, C, lanes, s_sum, s_sq, scratch);
   const int nch = lanes * 4;
   for (int i = threadIdx.x; i < nch; i += kBnThreads) {
     const int c = blockIdx.x * nch + i;
     if (c >= C) continue;
-    double ds = 0.0, dq = 0.0;
-    for (int sl = 0; sl < (int)gridDim.y; ++sl) {
-      ds += (double)__ldcg(&part[((long long)sl * 2 + 0) * C + c]);       // written by other SMs: read at L2
-      dq += (double)__ldcg(&part[((long long)sl * 2 + 1) * C + c]);
-    }
+    const double ds = s_sum[i], dq = s_sq[i];
     const double shift = (double)running_mean[c];
     const double ms = ds / (double)M;                             // mean of (x - shift)
     double var = dq / (double)M - ms * ms;                        // biased variance
@@ -233,15 +265,14 @@ bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ y, c
   __syncthreads();
   if (!last) return;
   __threadfence();
+  __shared__ double s_sum[128], s_sq[128];
+  __shared__ double4 scratch[2 * kBnThreads];
+  reduce_partials(part, (int)gridDim.y, C, lanes, s_sum, s_sq, scratch);
   const int nch = lanes * 4;
   for (int i = threadIdx.x; i < nch; i += kBnThreads) {
     const int c = blockIdx.x * nch + i;
     if (c >= C) continue;
-    double ds = 0.0, dq = 0.0;
-    for (int sl = 0; sl < (int)gridDim.y; ++sl) {
-      ds += (double)__ldcg(&part[((long long)sl * 2 + 0) * C + c]);       // written by other SMs: read at L2
-      dq += (double)__ldcg(&part[((long long)sl * 2 + 1) * C + c]);
-    }
+    const double ds = s_sum[i], dq = s_sq[i];
     dbeta[c] = (float)ds;
     dgamma[c] = (float)dq;
     c1[c] = (float)(ds / (double)M);

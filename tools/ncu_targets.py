@@ -68,6 +68,14 @@ if which in ("stage", "conv"):
     for _ in range(3):                      # layer-1 shape of ResNet-18/CIFAR at batch 64: staging (im2col, transposed im2col), GEMMs, split-K fold
         y = conv(x)
         y.backward(torch.ones_like(y))
+if which in ("bn",):
+    from cpd_b200.nn import BatchNormAct2d
+    bn = BatchNormAct2d(64, relu=True).cuda()
+    x = torch.randn(512, 64, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    r = torch.randn(512, 64, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    for _ in range(3):                      # the largest BatchNorm of ResNet-18/CIFAR at batch 512: 134 MB activations
+        y = bn(x, r)
+        y.backward(torch.ones_like(y))
 if which in ("allreduce_fake",):
     # the cross-GPU kernel told world = 8 with every peer aliased to this GPU (tools/fake_world.py): ncu can replay it
     import subprocess
