@@ -20,5 +20,23 @@ timeout 400 python tools/kernel_microbench.py > $OUT/microbench.json 2> $OUT/mic
 for fl in "" "--fused-bn" "--fused-bn --steal-grads --pipelined"; do tag=$(echo "x$fl" | tr -d ' -'); timeout 300 python bench.py --steps 30 --warmup 5 $fl > $OUT/bench_ours_$tag.json 2>> $OUT/bench.err; python -c "
 import json; d=json.loads(open('$OUT/bench_ours_$tag.json').read().strip().splitlines()[-1]); print('$fl', d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'])"; done
 timeout 300 python bench.py --model resnet18_quant --steps 10 --warmup 3 > $OUT/bench_quant_ours.json 2>> $OUT/bench.err; cut -c1-260 $OUT/bench_quant_ours.json
+echo "== launch list of resnet18_quant steps (eager, serialised under ncu: compare SHARES)"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches_quant.csv \
+   python bench.py --model resnet18_quant --steps 2 --warmup 3 --no-graph --fused-bn > $OUT/ncu_quant.log 2>&1; echo "ncu_rc=$?"; tail -2 $OUT/ncu_quant.log | cut -c1-200
+python - <<PY
+import csv, collections
+rows = list(csv.reader(open("$OUT/launches_quant.csv", errors="ignore")))
+hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+H = rows[hdr]; kn, mv = H.index("Kernel Name"), H.index("Metric Value")
+agg = collections.defaultdict(lambda: [0, 0.0])
+for r in rows[hdr + 1:]:
+    if len(r) > mv:
+        try: agg[r[kn][:110]][0] += 1; agg[r[kn][:110]][1] += float(r[mv].replace(",", ""))
+        except ValueError: pass
+tot = sum(v[1] for v in agg.values())
+print("total ms", tot / 1e6, "launches", sum(v[0] for v in agg.values()))
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
+    print("%5.1f%% %5d %9.1f us  %s" % (100 * v[1] / tot, v[0], v[1] / 1e3, k))
+PY
 python tools/summarize_profiles.py > $OUT/summarize.log 2>&1; tail -5 $OUT/summarize.log
 ls -la $OUT | head -30
