@@ -40,7 +40,7 @@ class _Arena:
 
 
 def _time_us(fn, iters: int, group) -> float:
-    for _ in range(3):
+    for _ in range(8):
         fn()
     dist.barrier(group=group)
     torch.cuda.synchronize()
@@ -87,18 +87,18 @@ def calibrate(grad_exp: int = 4, grad_man: int = 3, group=None, sizes: Optional[
                 print("[calibrate]", row, flush=True)
     finally:
         ws.close()
+    # crossovers, scanned from the LARGEST size down (one noisy small-size sample must not end the scan): raw keeps the
+    # buckets up to the largest size at which it still beats both packed variants; one-shot likewise against two-shot
     raw_max = 1024
-    for r in rows:                                             # largest size up to which raw is never beaten
+    for r in reversed(rows):
         if r["raw"] <= min(r["oneshot"], r[big]) * 1.02:
             raw_max = r["elems"]
-        else:
             break
     one_max = 64 * 1024
     wire_bytes = R.native.wire_bits(grad_exp, grad_man) // 8
-    for r in rows:
+    for r in reversed(rows):
         if r["oneshot"] <= r[big] * 1.02:
             one_max = r["elems"] * wire_bytes
-        else:
             break
     th = R.Thresholds(world, base.link_gbs, base.multicast, raw_max_elems=raw_max,
                       oneshot_max_bytes=one_max, source="calibrated")

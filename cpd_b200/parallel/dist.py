@@ -42,8 +42,11 @@ class Topology:
 
     @property
     def est_link_gbs(self) -> float:
-        """Per-direction NVLink bandwidth estimate per GPU (GB/s): links x per-link rate."""
-        per_link = {5: 50.0, 4: 25.0, 3: 25.0}.get(max((d.get("version", 0) for d in self.nvlink), default=0), 25.0)
+        """Per-direction NVLink bandwidth estimate per GPU (GB/s): links x per-link rate.  NVML reports the link
+        generation as an enum (nvmlNvlinkVersion_t: 1 = 1.0, 2 = 2.0, 3 = 2.2, 4 = 3.0, 5 = 3.1, 6 = 4.0, 7 = 5.0);
+        NVLink 5 (B200) moves 50 GB/s per link per direction, generations 2-4 move 25, NVLink 1 moves 20."""
+        ver = max((d.get("version", 0) for d in self.nvlink), default=0)
+        per_link = 50.0 if ver >= 7 else (20.0 if ver == 1 else 25.0)
         return self.nvlink_links * per_link
 
     def summary(self) -> str:

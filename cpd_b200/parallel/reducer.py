@@ -37,10 +37,15 @@ _ALGO = {"auto": native.ALGO_AUTO, "oneshot": native.ALGO_ONESHOT, "twoshot": na
 # + pack of a granule through pretruncate() + F2FP.SATFINITE, proven equal to the software cast on all 2^32 patterns
 # below the overflow band, tools/exhaustive_cast_check.sh) is ON by default; CPD_B200_PACK_HW=0 switches it off.
 _PROTO = 0x100 if os.environ.get("CPD_B200_PACK_HW", "1") == "1" else 0
-# experiments: only CTA 0 polls the peers' flags / plain loads for the peers' wire data / no extra fence before a flag
+# No explicit __threadfence_system() in front of a flag's st.release.sys (bit 11): the release is cumulative over what
+# CTA 0 observed through the grid barrier, so the fence is redundant; measured -1.5..-2 us per flag round (fake world W = 8:
+# one-shot 1 MB 27.5 -> 23.6 us; 2 real GPUs 24.0 -> 22.2 us), 91 cases + specials bit-exact on 2 GPUs.  ON by default;
+# CPD_B200_NO_EXTRA_FENCE=0 restores the belt-and-braces fence.
+_PROTO |= 0x800 if os.environ.get("CPD_B200_NO_EXTRA_FENCE", "1") == "1" else 0
+# experiments that did not pay: only CTA 0 polls the peers' flags (+0.5 us), plain instead of system-scope loads of the
+# peers' wire data (no gain on real peers)
 _PROTO |= 0x200 if os.environ.get("CPD_B200_POLL_CTA0", "0") == "1" else 0
 _PROTO |= 0x400 if os.environ.get("CPD_B200_WEAK_LOADS", "0") == "1" else 0
-_PROTO |= 0x800 if os.environ.get("CPD_B200_NO_EXTRA_FENCE", "0") == "1" else 0
 _FAULT_DELAY_RANK = int(os.environ.get("CPD_B200_FAULT_DELAY_RANK", "-1"))
 _FAULT_DELAY_CYCLES = float(os.environ.get("CPD_B200_FAULT_DELAY_CYCLES", "2e8"))
 MAX_TENSORS_PER_BUCKET = 1024
@@ -59,14 +64,16 @@ class Thresholds:
     hands over to two-shot / NVLS (2 (W - 1) / W B per element) when the byte difference outweighs the third flag
     round + grid barrier of the gather half."""
 
-    FLAG_ROUND_US = 8.0
+    FLAG_ROUND_US = 6.0       # one flag round + grid barrier on real peers (phase stamps: 4-7 us at W = 2, 7-9 at W = 8)
+    LINK_DERATE = 0.5         # share of the nominal link rate a latency-exposed peer read / fold sustains
 
     def __init__(self, world: int, link_gbs: float = 900.0, multicast: bool = True, raw_max_elems: Optional[int] = None,
                  oneshot_max_bytes: Optional[int] = None, source: str = "topology"):
         self.world, self.link_gbs, self.multicast, self.source = world, float(link_gbs) or 900.0, multicast, source
-        per_us = self.link_gbs * 1e3                      # bytes per microsecond per direction
+        per_us = self.link_gbs * 1e3 * self.LINK_DERATE   # bytes per microsecond per direction, derated
         w = max(world, 2)
         if raw_max_elems is None:
+            # W = 2: ~675 K elements (measured crossover between 256 K and 1 M); W = 8: ~96 K
             raw_max_elems = int(self.FLAG_ROUND_US * per_us / (4.0 * (w - 1)))
             raw_max_elems = max(1024, min(raw_max_elems, 1 << 20))
         if oneshot_max_bytes is None:
@@ -209,9 +216,13 @@ class GradReducer:
         th = self.thresholds
         has_mc = self.symm is not None and self.symm.has_multicast
         if self.plain_fp32:
-            if has_mc and b.numel * 4 > 64 * 1024:
-                return native.ALGO_NVLS_SUM                     # the switch does the sum (multimem.ld_reduce)
-            return native.ALGO_ONESHOT if (self.world <= 2 or b.numel * 4 <= th.oneshot_max_bytes) else native.ALGO_TWOSHOT
+            # fp32 on the wire: the one-shot costs what the raw variant costs, so it keeps the same size range; above it
+            # the NVSwitch does the sum (multimem.ld_reduce) where there is one, a two-shot fp32 fold otherwise
+            if b.numel <= th.raw_max_elems:
+                return native.ALGO_ONESHOT
+            if has_mc and self.world > 2:
+                return native.ALGO_NVLS_SUM
+            return native.ALGO_ONESHOT if self.world <= 2 else native.ALGO_TWOSHOT
         nbytes = b.numel * (self.wire // 8)
         if self.cfg.use_aps and b.numel <= th.raw_max_elems:
             return native.ALGO_ONESHOT_RAW              # latency-bound: one flag round, raw fp32 on the wire

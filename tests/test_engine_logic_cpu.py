@@ -73,7 +73,7 @@ def test_variant_selection_follows_the_measured_thresholds():
     from cpd_b200.ops import native
     from cpd_b200.parallel import reducer as R
     th8 = R.Thresholds(8, link_gbs=900.0)
-    assert 200_000 < th8.raw_max_elems < 300_000 and 1 << 20 <= th8.oneshot_max_bytes <= 4 << 20
+    assert 64_000 < th8.raw_max_elems < 200_000 and 512 << 10 <= th8.oneshot_max_bytes <= 2 << 20
     assert R.Thresholds(2, link_gbs=900.0).raw_max_elems > th8.raw_max_elems        # fewer peers: raw pays longer
     assert R.Thresholds(8, link_gbs=450.0).raw_max_elems < th8.raw_max_elems        # slower links: hand over earlier
     arena = ModelArena(list(_net().parameters()))
@@ -86,7 +86,7 @@ def test_variant_selection_follows_the_measured_thresholds():
     assert r.algo_for(bucket(th.oneshot_max_bytes)) == native.ALGO_ONESHOT            # 8-bit wire: bytes == elements
     assert r.algo_for(bucket(th.oneshot_max_bytes + 16)) == native.ALGO_NVLS
     r.plain_fp32 = True
-    assert r.algo_for(bucket(1 << 20)) == native.ALGO_NVLS_SUM
+    assert r.algo_for(bucket(1 << 20)) == native.ALGO_NVLS_SUM and r.algo_for(bucket(1024)) == native.ALGO_ONESHOT
     r.plain_fp32 = False
     r.symm = SimpleNamespace(has_multicast=False)
     assert r.algo_for(bucket(1 << 24)) == native.ALGO_TWOSHOT
