@@ -43,7 +43,12 @@ for f in sorted(glob.glob("$OUT/check_*.json")):
 PY
 echo "== calibration"; port=$((port + 1))
 timeout 200 $TR --master-port $port tools/calibrate_run.py > $OUT/calibrate.log 2>&1; echo "rc=$?"; grep -E "calibrate|thresholds" $OUT/calibrate.log | tail -8 | cut -c1-300
-for cfg in "resnet18:" "resnet18:--pipelined" "resnet18:--overlap" "resnet18:--overlap --comm-ctas 148 --bucket-mb 24" "resnet18:--overlap --comm-ctas 74 --bucket-mb 24" "davidnet:" "resnet50:" "resnet18_quant:"; do
+if [ "$MODE" = full ]; then
+  CFGS=("resnet18:" "resnet18:--pipelined" "resnet18:--overlap" "resnet18:--overlap --comm-ctas 148 --bucket-mb 24" "resnet18:--overlap --comm-ctas 74 --bucket-mb 24" "davidnet:" "resnet50:" "resnet18_quant:")
+else
+  CFGS=("resnet18:" "resnet18:--overlap --comm-ctas 148 --bucket-mb 24" "resnet50:" "davidnet:" "resnet18_quant:")
+fi
+for cfg in "${CFGS[@]}"; do
   m=${cfg%%:*}; fl=${cfg#*:}; tag=$(echo "$m$fl" | tr -d ' -')
   port=$((port + 1))
   echo "== bench ours $m $fl N=$N"
