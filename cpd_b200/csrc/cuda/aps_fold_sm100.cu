@@ -31,7 +31,7 @@ struct SrcPtrs { const float* p[kMaxLocalSrc]; };
 constexpr int kVecPerThread = 4;     // 4 x 256 threads x 4 floats = 4096 = CHUNK_ELEMS
 
 template <class F, bool KAHAN>
-__global__ void __launch_bounds__(kFoldThreads, 3)
+__global__ void __launch_bounds__(kFoldThreads, 4)
 aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__ chunks,
                       int n_chunks, int T, int T_cap, F fmt, bool use_aps, float world_mult,
                       unsigned* __restrict__ ws, int* __restrict__ shifts_out) {
@@ -54,19 +54,6 @@ aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__
   if (use_aps) {
     unsigned m = 0u;
     int cur_tensor = -1;
-    // one source (world size 1, the hot single-GPU path): chunk c + 1's vectors are requested before chunk c is reduced,
-    // so the ~1 us DRAM latency of the CTA's 4-5 sequential chunks overlaps instead of adding up
-    uint4 pre[kVecPerThread];
-    const bool single = W == 1;
-    if (single && c_lo < c_hi) {
-      const Chunk ck = chunks[c_lo];
-      const uint4* base = reinterpret_cast<const uint4*>(s_src[0] + ck.start);
-#pragma unroll
-      for (int k = 0; k < kVecPerThread; ++k) {
-        const int v = threadIdx.x + k * kFoldThreads;
-        pre[k] = v < (ck.len >> 2) ? base[v] : make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
     for (int c = c_lo; c < c_hi; ++c) {
       const Chunk ck = chunks[c];
       const int nvec = ck.len >> 2;
@@ -77,24 +64,6 @@ aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__
         }
         cur_tensor = ck.tensor;
         m = 0u;
-      }
-      if (single) {
-        uint4 x[kVecPerThread];
-#pragma unroll
-        for (int k = 0; k < kVecPerThread; ++k) x[k] = pre[k];
-        if (c + 1 < c_hi) {
-          const Chunk cn = chunks[c + 1];
-          const uint4* nb = reinterpret_cast<const uint4*>(s_src[0] + cn.start);
-#pragma unroll
-          for (int k = 0; k < kVecPerThread; ++k) {
-            const int v = threadIdx.x + k * kFoldThreads;
-            pre[k] = v < (cn.len >> 2) ? nb[v] : make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < kVecPerThread; ++k)
-          m = max(max(m, x[k].x & 0x7FFFFFFFu), max(x[k].y & 0x7FFFFFFFu, max(x[k].z & 0x7FFFFFFFu, x[k].w & 0x7FFFFFFFu)));
-        continue;
       }
       for (int r = 0; r < W; ++r) {
         const uint4* base = reinterpret_cast<const uint4*>(s_src[r] + ck.start);
@@ -116,16 +85,6 @@ aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__
     grid_barrier(bar);
   }
 
-  float4 preb[kVecPerThread];
-  if (W == 1 && c_lo < c_hi) {
-    const Chunk ck = chunks[c_lo];
-    const float4* base = reinterpret_cast<const float4*>(s_src[0] + ck.start);
-#pragma unroll
-    for (int k = 0; k < kVecPerThread; ++k) {
-      const int v = threadIdx.x + k * kFoldThreads;
-      preb[k] = v < (ck.len >> 2) ? base[v] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
   for (int c = c_lo; c < c_hi; ++c) {
     const Chunk ck = chunks[c];
     const int nvec = ck.len >> 2;
@@ -145,24 +104,10 @@ aps_fold_local_kernel(SrcPtrs srcs, int W, float* out, const Chunk* __restrict__
     for (int r = 0; r < W; ++r) {
       const float4* base = reinterpret_cast<const float4*>(s_src[r] + ck.start);
       float4 g4[kVecPerThread];
-      if (W == 1) {                              // prefetched while the previous chunk was being cast; request the next one now
 #pragma unroll
-        for (int k = 0; k < kVecPerThread; ++k) g4[k] = preb[k];
-        if (c + 1 < c_hi) {
-          const Chunk cn = chunks[c + 1];
-          const float4* nb = reinterpret_cast<const float4*>(s_src[0] + cn.start);
-#pragma unroll
-          for (int k = 0; k < kVecPerThread; ++k) {
-            const int v = threadIdx.x + k * kFoldThreads;
-            preb[k] = v < (cn.len >> 2) ? nb[v] : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < kVecPerThread; ++k) {
-          const int v = threadIdx.x + k * kFoldThreads;
-          g4[k] = v < nvec ? base[v] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+      for (int k = 0; k < kVecPerThread; ++k) {
+        const int v = threadIdx.x + k * kFoldThreads;
+        g4[k] = v < nvec ? base[v] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int k = 0; k < kVecPerThread; ++k) {
@@ -216,7 +161,7 @@ void aps_fold_local_cuda(const float* const* srcs_host, int W, float* out, const
   if (n_chunks <= 0 || W <= 0) return;
   SrcPtrs sp;
   for (int r = 0; r < kMaxLocalSrc; ++r) sp.p[r] = r < W ? srcs_host[r] : nullptr;
-  int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1) * 3;   // 3 co-resident CTAs / SM (launch bounds; the prefetch registers)
+  int grid = max_ctas > 0 ? max_ctas : device_sm_count(-1) * 4;   // 4 co-resident CTAs / SM (launch bounds)
   if (grid > n_chunks) grid = n_chunks;
   CPD_DISPATCH_FORMAT(e, m, rounding, FMT, {
     if (kahan)
