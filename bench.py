@@ -44,7 +44,11 @@ CONFIGS = {
 # Engine options of the "ours" arm and their defaults = what measured fastest on the B200 box (profiles/README.md);
 # every one has a --no-... switch.  They change HOW the step is executed, never WHAT it computes (same architecture,
 # fp32/TF32 compute, same batch, same gradient format).
-DEFAULT_FLAGS = dict(overlap=False, pipelined=False, fused_bn=False, steal_grads=False)
+# Measured on one B200, ResNet-18 config (profiles/bench/r2t3_*): stock BN + arena accumulation 69 230 img/s (e2e 67 884);
+# fused BN 72 222; fused BN + stolen gradients + pipelined input copy 73 697 (e2e 73 287).  Overlapped bucketed reduction
+# LOSES on this workload (1 GPU 7.57 vs 7.29 ms, 2 GPUs 7.53-7.84 vs 7.48 ms: the comm grid slows the convolutions it
+# co-runs with by more than the ~0.1 ms of all-reduce it hides), so it stays off.
+DEFAULT_FLAGS = dict(overlap=False, pipelined=True, fused_bn=True, steal_grads=True)
 
 # published reference numbers: only ResNet-50 has one (<= ~1068 img/s on 8xV100, derived bound)
 PUBLISHED = {"resnet50": 1068.0}
@@ -150,8 +154,7 @@ def run_ours(args, cfg):
                          algo=args.algo, overlap=args.overlap, bucket_mb=args.bucket_mb, emulate_node=args.emulate_node,
                          comm_ctas=args.comm_ctas)
     model_kw = dict(exp=cfg["gemm_exp"], man=cfg["gemm_man"], mode="tile", operands="bf16") if "gemm_exp" in cfg else {}
-    if args.fused_bn:
-        model_kw["fused_bn"] = True              # BatchNorm + shortcut add + ReLU in this repo's kernels (same arithmetic)
+    model_kw["fused_bn"] = bool(args.fused_bn)   # BatchNorm + shortcut add + ReLU in this repo's kernels (same arithmetic)
     model = create_model(cfg["arch"], **model_kw)
     wd_mult = bn_bias_no_decay(model.named_parameters()) if args.model == "resnet50" else None
     eng = TrainEngine(model, pc, batch_size=cfg["batch"], input_shape=cfg["shape"], lr=cfg["lr"], momentum=0.9,

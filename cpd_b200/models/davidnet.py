@@ -87,7 +87,7 @@ def _residual(nodes, name, src, c, fused_bn=False):
 
 
 def davidnet(channels=(64, 128, 256, 512), num_classes: int = 10, logit_scale: float = 0.125,
-             res_layers=(1, 3), fused_bn: bool = False) -> GraphNet:
+             res_layers=(1, 3), fused_bn: bool = True) -> GraphNet:
     nodes: List = []
     cur = _conv_bn(nodes, "prep", "input", 3, channels[0], fused_bn=fused_bn)
     for i in (1, 2, 3):

@@ -1,6 +1,8 @@
 """ResNet-18 for 32x32 inputs (the reference's CIFAR workload: example/ResNet18/models/
 resnet18_cifar.py — 3x3 stem, no max-pool, 4 stages x 2 basic blocks, avg-pool 4, fc).
-62 parameter tensors, 11 173 962 parameters."""
+62 parameter tensors, 11 173 962 parameters.  ``fused_bn`` (default): the BatchNorm layers are ``BatchNormAct2d`` -
+the same parameters, buffers and arithmetic with the ReLU and the shortcut add folded into this repo's kernels on
+channels_last fp32 CUDA tensors (stock ops everywhere else)."""
 from __future__ import annotations
 
 import torch
@@ -68,16 +70,16 @@ class ResNetCifar(nn.Module):
         return self.fc(x)
 
 
-def resnet18_cifar(num_classes: int = 10, fused_bn: bool = False) -> ResNetCifar:
+def resnet18_cifar(num_classes: int = 10, fused_bn: bool = True) -> ResNetCifar:
     return ResNetCifar((2, 2, 2, 2), num_classes=num_classes, fused_bn=fused_bn)
 
 
-def resnet34_cifar(num_classes: int = 10, fused_bn: bool = False) -> ResNetCifar:
+def resnet34_cifar(num_classes: int = 10, fused_bn: bool = True) -> ResNetCifar:
     return ResNetCifar((3, 4, 6, 3), num_classes=num_classes, fused_bn=fused_bn)
 
 
 def resnet18_cifar_quant(num_classes: int = 10, exp: int = 5, man: int = 10, mode: str = "tile", operands=None, k_slice: int = 128,
-                         kahan: bool = False, fused_bn: bool = False) -> ResNetCifar:
+                         kahan: bool = False, fused_bn: bool = True) -> ResNetCifar:
     """The same network with EVERY convolution a ``Quant_Conv`` (CPDtorch/quant/quant_module.py:88-139): forward,
     data-gradient and weight-gradient GEMMs keep their accumulator at (exp, man).  ``mode="tile"`` runs them on the
     tcgen05 kernels with fused im2col/cast staging, ``"exact"`` is the reference's per-MAC semantics.  The 10-class

@@ -95,17 +95,17 @@ class ResNet(nn.Module):
         return self.fc(x)
 
 
-def resnet18(num_classes=1000, fused_bn=False):
+def resnet18(num_classes=1000, fused_bn=True):
     return ResNet(Basic, (2, 2, 2, 2), num_classes, fused_bn=fused_bn)
 
 
-def resnet34(num_classes=1000, fused_bn=False):
+def resnet34(num_classes=1000, fused_bn=True):
     return ResNet(Basic, (3, 4, 6, 3), num_classes, fused_bn=fused_bn)
 
 
-def resnet50(num_classes=1000, fused_bn=False):
+def resnet50(num_classes=1000, fused_bn=True):
     return ResNet(Bottleneck, (3, 4, 6, 3), num_classes, fused_bn=fused_bn)
 
 
-def resnet101(num_classes=1000, fused_bn=False):
+def resnet101(num_classes=1000, fused_bn=True):
     return ResNet(Bottleneck, (3, 4, 23, 3), num_classes, fused_bn=fused_bn)

@@ -48,7 +48,7 @@ class TrainEngine:
                  loss_scale: float = 1.0, channels_last: bool = True, cuda_graph: bool = True,
                  fold_single: bool = False, device: Optional[torch.device] = None, master_weights: bool = True,
                  lars_eps: float = 0.0, warmup_steps: int = 3, amp_dtype: Optional[torch.dtype] = None,
-                 steal_grads: bool = False):
+                 steal_grads: bool = True):
         self.cfg = cfg
         self.distributed = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size() if self.distributed else 1

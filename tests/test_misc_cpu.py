@@ -40,8 +40,10 @@ def test_timer_and_scalar_writer(tmp_path):
 def test_topology_record_and_summary():
     topo = Topology(device_count=2, devices=[{"name": "B200"}, {"name": "B200"}],
                     p2p=[[{"access": True}, {"access": True}], [{"access": True}, {"access": True}]],
-                    nvlink=[{"active_links": 18, "version": 5}, {"active_links": 18, "version": 5}], multicast=True)
+                    nvlink=[{"active_links": 18, "version": 7}, {"active_links": 18, "version": 7}], multicast=True)
+    # NVML's link-generation enum: 7 = NVLink 5 (what a B200 reports), 50 GB/s per link per direction; 6 = NVLink 4, 25 GB/s
     assert topo.all_p2p and topo.nvlink_links == 18 and topo.est_link_gbs == 900.0
+    assert Topology(device_count=1, nvlink=[{"active_links": 18, "version": 6}]).est_link_gbs == 450.0
     assert "2x B200" in topo.summary() and "multicast=True" in topo.summary()
     topo.p2p[0][1]["access"] = False
     assert not topo.all_p2p and "partial" in topo.summary()
