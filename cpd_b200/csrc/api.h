@@ -123,9 +123,11 @@ void colsum_quantize_cuda(const float* x, long long rows, int cols, long long ld
 long long bn_workspace_floats(long long M, int C);
 int bn_act_forward_cuda(const float* x, const float* res, float* y, long long M, int C, const float* gamma, const float* beta,
                         float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
-                        bool relu, float* stats, float* workspace, cudaStream_t st);
-int bn_act_backward_cuda(const float* dy, const float* y, const float* x, float* dx, float* dres, long long M, int C,
-                         const float* gamma, const float* stats, bool relu, float* grads, float* workspace, cudaStream_t st);
+                        bool relu, float* stats, float* workspace, unsigned* relu_mask, cudaStream_t st);
+// relu_mask (optional, M*C/32 words, M*C % 32 == 0): 1 bit per element written by the forward apply; the backward then
+// reads it instead of y (either y or relu_mask must be given when relu)
+int bn_act_backward_cuda(const float* dy, const float* y, const unsigned* relu_mask, const float* x, float* dx, float* dres, long long M,
+                         int C, const float* gamma, const float* stats, bool relu, float* grads, float* workspace, cudaStream_t st);
 
 // tcgen05 / TMEM / TMA GEMM with per-K-slice accumulator re-quantisation.
 // operand_mode: 0 = bf16 operands (kind::f16), 1 = tf32 (kind::tf32), 2 = e4m3, 3 = e5m2

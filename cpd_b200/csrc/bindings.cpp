@@ -132,17 +132,17 @@ PYBIND11_MODULE(_C, m) {
   // fused BatchNorm + residual + ReLU (training), channels_last fp32
   m.def("bn_workspace_floats", [](int64_t M, int C) { return (int64_t)cpd::bn_workspace_floats(M, C); });
   m.def("bn_act_forward_cuda", [](uptr x, uptr res, uptr y, int64_t M, int C, uptr gamma, uptr beta, uptr rmean, uptr rvar, uptr nbt,
-                                  double momentum, double eps, bool relu, uptr stats, uptr ws, uptr stream) {
+                                  double momentum, double eps, bool relu, uptr stats, uptr ws, uptr relu_mask, uptr stream) {
     int rc = cpd::bn_act_forward_cuda(P<const float>(x), P<const float>(res), P<float>(y), M, C, P<const float>(gamma), P<const float>(beta),
                                       P<float>(rmean), P<float>(rvar), P<long long>(nbt), (float)momentum, (float)eps, relu, P<float>(stats),
-                                      P<float>(ws), S(stream));
+                                      P<float>(ws), P<unsigned>(relu_mask), S(stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);            // two kernels per call
     check_launch("bn_act_forward");
     return rc;
   });
-  m.def("bn_act_backward_cuda", [](uptr dy, uptr y, uptr x, uptr dx, uptr dres, int64_t M, int C, uptr gamma, uptr stats, bool relu, uptr grads,
-                                   uptr ws, uptr stream) {
-    int rc = cpd::bn_act_backward_cuda(P<const float>(dy), P<const float>(y), P<const float>(x), P<float>(dx), P<float>(dres), M, C,
+  m.def("bn_act_backward_cuda", [](uptr dy, uptr y, uptr relu_mask, uptr x, uptr dx, uptr dres, int64_t M, int C, uptr gamma, uptr stats,
+                                   bool relu, uptr grads, uptr ws, uptr stream) {
+    int rc = cpd::bn_act_backward_cuda(P<const float>(dy), P<const float>(y), P<const unsigned>(relu_mask), P<const float>(x), P<float>(dx), P<float>(dres), M, C,
                                        P<const float>(gamma), P<const float>(stats), relu, P<float>(grads), P<float>(ws), S(stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     check_launch("bn_act_backward");

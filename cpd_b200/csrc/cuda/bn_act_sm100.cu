@@ -182,8 +182,12 @@ bn_stats_kernel(const float* __restrict__ x, long long M, int C, long long rows_
 template <bool RELU, bool RES>
 __global__ void __launch_bounds__(kBnThreads)
 bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ y, long long n4, int C4,
-                const float* __restrict__ scale, const float* __restrict__ bias) {
+                const float* __restrict__ scale, const float* __restrict__ bias, unsigned* __restrict__ mask) {
   const long long stride = (long long)gridDim.x * kBnThreads;
+  // ReLU bitmask for the backward pass (1 bit per element instead of re-reading y: 32x less traffic there): 8 consecutive
+  // threads hold 8 consecutive vectors = 32 elements = one word.  n4 % 8 == 0 (checked on the host), so the 8 lanes of a
+  // group are all in range or all out of range and the group-wide shuffles are well defined.
+  const unsigned gmask = 0xFFu << (threadIdx.x & 24);
   // two independent vectors per thread per iteration: 32-64 B in flight per thread keeps HBM busy at 2048 threads / SM
   for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < n4; i += 2 * stride) {
     const long long j = i + stride;
@@ -204,7 +208,17 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, floa
         const float4 r = h ? r1 : r0;
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
-      if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      if (RELU) {
+        if (mask) {
+          unsigned nib = (o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u);
+          nib <<= 4 * (threadIdx.x & 7);
+          nib |= __shfl_xor_sync(gmask, nib, 1);
+          nib |= __shfl_xor_sync(gmask, nib, 2);
+          nib |= __shfl_xor_sync(gmask, nib, 4);
+          if ((threadIdx.x & 7) == 0) mask[e >> 3] = nib;
+        }
+        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+      }
       *reinterpret_cast<float4*>(y + e * 4) = o;
     }
   }
@@ -214,7 +228,8 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, floa
 // coef out: c1[C] = mean(dz), c2[C] = mean(dz * xhat); dgamma[C], dbeta[C]
 template <bool RELU>
 __global__ void __launch_bounds__(kBnThreads)
-bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, long long M, int C,
+bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ y, const unsigned* __restrict__ mask,
+                    const float* __restrict__ x, long long M, int C,
                     long long rows_per_slab, int lanes, const float* __restrict__ mean, const float* __restrict__ rstd,
                     float* __restrict__ part, unsigned* __restrict__ counters, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2) {
@@ -233,6 +248,7 @@ bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ y, c
     // 4 rows x (dy, x, y) = up to 12 independent 16-byte loads in flight per thread
     for (long long r = r0 + ty; r < r1; r += 4LL * rows_par) {
       float4 g[4], xv[4], yv[4];
+      unsigned mb[4];
       bool ok[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -241,14 +257,22 @@ bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ y, c
         const long long a = (ok[j] ? rj : r) * C + c0;
         g[j] = ld4(dy + a);
         xv[j] = ld4(x + a);
-        if (RELU) yv[j] = ld4(y + a);
+        if (RELU) {
+          if (mask) mb[j] = (mask[a >> 5] >> (4 * (int)((a >> 2) & 7))) & 0xFu;       // vector a/4: word (a/4)/8, nibble (a/4)%8
+          else yv[j] = ld4(y + a);
+        }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (!ok[j]) continue;
         if (RELU) {
-          g[j].x = yv[j].x > 0.f ? g[j].x : 0.f; g[j].y = yv[j].y > 0.f ? g[j].y : 0.f;
-          g[j].z = yv[j].z > 0.f ? g[j].z : 0.f; g[j].w = yv[j].w > 0.f ? g[j].w : 0.f;
+          if (mask) {
+            g[j].x = (mb[j] & 1u) ? g[j].x : 0.f; g[j].y = (mb[j] & 2u) ? g[j].y : 0.f;
+            g[j].z = (mb[j] & 4u) ? g[j].z : 0.f; g[j].w = (mb[j] & 8u) ? g[j].w : 0.f;
+          } else {
+            g[j].x = yv[j].x > 0.f ? g[j].x : 0.f; g[j].y = yv[j].y > 0.f ? g[j].y : 0.f;
+            g[j].z = yv[j].z > 0.f ? g[j].z : 0.f; g[j].w = yv[j].w > 0.f ? g[j].w : 0.f;
+          }
         }
         s.x += g[j].x; s.y += g[j].y; s.z += g[j].z; s.w += g[j].w;
         q.x += g[j].x * (xv[j].x - mu.x) * rs.x; q.y += g[j].y * (xv[j].y - mu.y) * rs.y;
@@ -289,7 +313,8 @@ bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ y, c
 // ---- backward: apply ----------------------------------------------------------------------------------------------
 template <bool RELU, bool RES>
 __global__ void __launch_bounds__(kBnThreads)
-bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, float* __restrict__ dx,
+bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, const unsigned* __restrict__ mask,
+                    const float* __restrict__ x, float* __restrict__ dx,
                     float* __restrict__ dres, long long n4, int C4, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ c1, const float* __restrict__ c2) {
   const long long stride = (long long)gridDim.x * kBnThreads;
@@ -298,8 +323,13 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, c
     float4 g = ld4(dy + i * 4);
     const float4 v = ld4(x + i * 4);
     if (RELU) {
-      const float4 o = ld4(y + i * 4);
-      g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+      if (mask) {
+        const unsigned mb = (mask[i >> 3] >> (4 * (int)(i & 7))) & 0xFu;
+        g.x = (mb & 1u) ? g.x : 0.f; g.y = (mb & 2u) ? g.y : 0.f; g.z = (mb & 4u) ? g.z : 0.f; g.w = (mb & 8u) ? g.w : 0.f;
+      } else {
+        const float4 o = ld4(y + i * 4);
+        g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+      }
     }
     if (RES) *reinterpret_cast<float4*>(dres + i * 4) = g;
     const float4 mu = ld4(mean + c0), rs = ld4(rstd + c0), ga = ld4(gamma + c0), a = ld4(c1 + c0), b = ld4(c2 + c0);
@@ -328,7 +358,7 @@ long long bn_workspace_floats(long long M, int C) {
 
 int bn_act_forward_cuda(const float* x, const float* res, float* y, long long M, int C, const float* gamma, const float* beta,
                         float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
-                        bool relu, float* stats, float* workspace, cudaStream_t st) {
+                        bool relu, float* stats, float* workspace, unsigned* relu_mask, cudaStream_t st) {
   if (M <= 0 || C <= 0) return 0;
   if (C % 4) return -1;
   const int sms = device_sm_count(-1);
@@ -340,17 +370,18 @@ int bn_act_forward_cuda(const float* x, const float* res, float* y, long long M,
                                                                    momentum, eps, part, counters, mean, rstd, scale, bias,
                                                                    num_batches_tracked);
   const long long n4 = M * C / 4;
+  if (relu_mask && (n4 % 8)) return -2;                  // the bitmask path packs 8 vectors per word
   const int grid = ew_grid(n4, sms);
-  if (relu && res) bn_apply_kernel<true, true><<<grid, kBnThreads, 0, st>>>(x, res, y, n4, C / 4, scale, bias);
-  else if (relu) bn_apply_kernel<true, false><<<grid, kBnThreads, 0, st>>>(x, res, y, n4, C / 4, scale, bias);
-  else if (res) bn_apply_kernel<false, true><<<grid, kBnThreads, 0, st>>>(x, res, y, n4, C / 4, scale, bias);
-  else bn_apply_kernel<false, false><<<grid, kBnThreads, 0, st>>>(x, res, y, n4, C / 4, scale, bias);
+  if (relu && res) bn_apply_kernel<true, true><<<grid, kBnThreads, 0, st>>>(x, res, y, n4, C / 4, scale, bias, relu_mask);
+  else if (relu) bn_apply_kernel<true, false><<<grid, kBnThreads, 0, st>>>(x, res, y, n4, C / 4, scale, bias, relu_mask);
+  else if (res) bn_apply_kernel<false, true><<<grid, kBnThreads, 0, st>>>(x, res, y, n4, C / 4, scale, bias, nullptr);
+  else bn_apply_kernel<false, false><<<grid, kBnThreads, 0, st>>>(x, res, y, n4, C / 4, scale, bias, nullptr);
   return 0;
 }
 
 // grads: float[4 * C] = dgamma | dbeta | c1 | c2
-int bn_act_backward_cuda(const float* dy, const float* y, const float* x, float* dx, float* dres, long long M, int C,
-                         const float* gamma, const float* stats, bool relu, float* grads, float* workspace, cudaStream_t st) {
+int bn_act_backward_cuda(const float* dy, const float* y, const unsigned* relu_mask, const float* x, float* dx, float* dres, long long M,
+                         int C, const float* gamma, const float* stats, bool relu, float* grads, float* workspace, cudaStream_t st) {
   if (M <= 0 || C <= 0) return 0;
   if (C % 4) return -1;
   const int sms = device_sm_count(-1);
@@ -360,17 +391,17 @@ int bn_act_backward_cuda(const float* dy, const float* y, const float* x, float*
   const float *mean = stats, *rstd = stats + C;
   float *dgamma = grads, *dbeta = grads + C, *c1 = grads + 2 * C, *c2 = grads + 3 * C;
   if (relu)
-    bn_bwd_stats_kernel<true><<<dim3(g.ctiles, g.slabs), kBnThreads, 0, st>>>(dy, y, x, M, C, g.rows_per_slab, g.lanes, mean, rstd, part,
+    bn_bwd_stats_kernel<true><<<dim3(g.ctiles, g.slabs), kBnThreads, 0, st>>>(dy, y, relu_mask, x, M, C, g.rows_per_slab, g.lanes, mean, rstd, part,
                                                                                 counters, dgamma, dbeta, c1, c2);
   else
-    bn_bwd_stats_kernel<false><<<dim3(g.ctiles, g.slabs), kBnThreads, 0, st>>>(dy, y, x, M, C, g.rows_per_slab, g.lanes, mean, rstd, part,
+    bn_bwd_stats_kernel<false><<<dim3(g.ctiles, g.slabs), kBnThreads, 0, st>>>(dy, y, nullptr, x, M, C, g.rows_per_slab, g.lanes, mean, rstd, part,
                                                                                  counters, dgamma, dbeta, c1, c2);
   const long long n4 = M * C / 4;
   const int grid = ew_grid(n4, sms);
-  if (relu && dres) bn_bwd_apply_kernel<true, true><<<grid, kBnThreads, 0, st>>>(dy, y, x, dx, dres, n4, C / 4, mean, rstd, gamma, c1, c2);
-  else if (relu) bn_bwd_apply_kernel<true, false><<<grid, kBnThreads, 0, st>>>(dy, y, x, dx, dres, n4, C / 4, mean, rstd, gamma, c1, c2);
-  else if (dres) bn_bwd_apply_kernel<false, true><<<grid, kBnThreads, 0, st>>>(dy, y, x, dx, dres, n4, C / 4, mean, rstd, gamma, c1, c2);
-  else bn_bwd_apply_kernel<false, false><<<grid, kBnThreads, 0, st>>>(dy, y, x, dx, dres, n4, C / 4, mean, rstd, gamma, c1, c2);
+  if (relu && dres) bn_bwd_apply_kernel<true, true><<<grid, kBnThreads, 0, st>>>(dy, y, relu_mask, x, dx, dres, n4, C / 4, mean, rstd, gamma, c1, c2);
+  else if (relu) bn_bwd_apply_kernel<true, false><<<grid, kBnThreads, 0, st>>>(dy, y, relu_mask, x, dx, dres, n4, C / 4, mean, rstd, gamma, c1, c2);
+  else if (dres) bn_bwd_apply_kernel<false, true><<<grid, kBnThreads, 0, st>>>(dy, y, nullptr, x, dx, dres, n4, C / 4, mean, rstd, gamma, c1, c2);
+  else bn_bwd_apply_kernel<false, false><<<grid, kBnThreads, 0, st>>>(dy, y, nullptr, x, dx, dres, n4, C / 4, mean, rstd, gamma, c1, c2);
   return 0;
 }
 

@@ -26,20 +26,23 @@ class _BNActFn(torch.autograd.Function):
         M = B * H * W
         y = torch.empty_like(x)                                  # keeps the channels_last strides
         stats = torch.empty(4 * C, dtype=torch.float32, device=x.device)
+        # 1 bit per element for the backward's ReLU mask (instead of re-reading y there): needs whole 32-element words
+        mask = torch.empty(M * C // 32, dtype=torch.int32, device=x.device) if (relu and (M * C) % 32 == 0) else None
         with torch.cuda.device(x.device):
             rc = native._C.bn_act_forward_cuda(x.data_ptr(), 0 if res is None else res.data_ptr(), y.data_ptr(), M, C, weight.data_ptr(),
                                                bias.data_ptr(), running_mean.data_ptr(), running_var.data_ptr(),
                                                0 if nbt is None else nbt.data_ptr(), float(momentum), float(eps), bool(relu),
-                                               stats.data_ptr(), ws.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
+                                               stats.data_ptr(), ws.data_ptr(), 0 if mask is None else mask.data_ptr(),
+                                               torch.cuda.current_stream(x.device).cuda_stream)
         if rc != 0:
             raise RuntimeError(f"bn_act_forward: rejected (code {rc})")
-        ctx.save_for_backward(x, y if relu else None, weight, stats)
+        ctx.save_for_backward(x, y if (relu and mask is None) else None, weight, stats, mask)
         ctx.relu, ctx.has_res, ctx.ws = bool(relu), res is not None, ws
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, weight, stats = ctx.saved_tensors
+        x, y, weight, stats, mask = ctx.saved_tensors
         B, C, H, W = x.shape
         M = B * H * W
         if not dy.is_contiguous(memory_format=torch.channels_last):
@@ -48,7 +51,8 @@ class _BNActFn(torch.autograd.Function):
         dres = torch.empty_like(x) if (ctx.has_res and ctx.needs_input_grad[1]) else None
         grads = torch.empty(4 * C, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            rc = native._C.bn_act_backward_cuda(dy.data_ptr(), 0 if y is None else y.data_ptr(), x.data_ptr(), dx.data_ptr(),
+            rc = native._C.bn_act_backward_cuda(dy.data_ptr(), 0 if y is None else y.data_ptr(), 0 if mask is None else mask.data_ptr(),
+                                                x.data_ptr(), dx.data_ptr(),
                                                 0 if dres is None else dres.data_ptr(), M, C, weight.data_ptr(), stats.data_ptr(),
                                                 ctx.relu, grads.data_ptr(), ctx.ws.data_ptr(),
                                                 torch.cuda.current_stream(x.device).cuda_stream)
