@@ -16,7 +16,12 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import os
+
 from ..ops import native
+
+# 1-bit ReLU mask for the backward pass instead of re-reading y (CPD_B200_BN_MASK=0 switches it off)
+_USE_MASK = os.environ.get("CPD_B200_BN_MASK", "0") == "1"
 
 
 class _BNActFn(torch.autograd.Function):
@@ -27,7 +32,7 @@ class _BNActFn(torch.autograd.Function):
         y = torch.empty_like(x)                                  # keeps the channels_last strides
         stats = torch.empty(4 * C, dtype=torch.float32, device=x.device)
         # 1 bit per element for the backward's ReLU mask (instead of re-reading y there): needs whole 32-element words
-        mask = torch.empty(M * C // 32, dtype=torch.int32, device=x.device) if (relu and (M * C) % 32 == 0) else None
+        mask = torch.empty(M * C // 32, dtype=torch.int32, device=x.device) if (_USE_MASK and relu and (M * C) % 32 == 0) else None
         with torch.cuda.device(x.device):
             rc = native._C.bn_act_forward_cuda(x.data_ptr(), 0 if res is None else res.data_ptr(), y.data_ptr(), M, C, weight.data_ptr(),
                                                bias.data_ptr(), running_mean.data_ptr(), running_var.data_ptr(),
