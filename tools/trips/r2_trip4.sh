@@ -5,6 +5,9 @@ set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 OUT=gpurun_out/r2t4; mkdir -p $OUT
 echo "== full GPU suite"; timeout 1500 python -m pytest tests -q -m gpu -x > $OUT/pytest_gpu.log 2>&1; echo "rc=$?"; tail -8 $OUT/pytest_gpu.log
+echo "== fused BN with the 1-bit ReLU mask"; CPD_B200_BN_MASK=1 timeout 400 python -m pytest tests/test_gpu_fused_bn.py -q -m gpu > $OUT/pytest_bn_mask.log 2>&1; echo "rc=$?"; tail -3 $OUT/pytest_bn_mask.log
+CPD_B200_BN_MASK=1 timeout 300 python bench.py --steps 30 --warmup 5 > $OUT/bench_ours_bnmask.json 2>> $OUT/bench.err; python -c "
+import json; d=json.loads(open('$OUT/bench_ours_bnmask.json').read().strip().splitlines()[-1]); print('ours [BN mask]', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'])"
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "rc=$?"; tail -3 $OUT/smoke.log
 echo "== smoke under ncu"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1000 --csv --log-file $OUT/launches_smoke.csv \
    python -c "import __graft_entry__ as g; g.smoke()" > $OUT/ncu_smoke.log 2>&1; echo "ncu_rc=$?"; grep -o "cpd::[<>a-z_0-9:]*" $OUT/launches_smoke.csv | sort | uniq -c
