@@ -49,6 +49,7 @@ _PROTO |= 0x400 if os.environ.get("CPD_B200_WEAK_LOADS", "0") == "1" else 0
 _FAULT_DELAY_RANK = int(os.environ.get("CPD_B200_FAULT_DELAY_RANK", "-1"))
 _FAULT_DELAY_CYCLES = float(os.environ.get("CPD_B200_FAULT_DELAY_CYCLES", "2e8"))
 MAX_TENSORS_PER_BUCKET = 1024
+NVLS_SUM_MAX_BYTES = 128 << 20
 # a peer that does not show up within this many SM cycles (~5 min at 1.9 GHz; NCCL's watchdog default is 10 min) makes
 # the kernel poison its outputs (NaN) and raise the status word; tests shorten it
 DEFAULT_TIMEOUT_CYCLES = 600_000_000_000
@@ -255,6 +256,11 @@ class GradReducer:
                             workspace=self.local_ws, shifts_out=self.shifts[i], max_ctas=self.ctas_for(i),
                             rounding=self.rounding)
         elif self.mode == "fused":
+            if self.plain_fp32 and b.numel * 4 > NVLS_SUM_MAX_BYTES and cfg.algo == "auto":
+                # plain fp32 sum of a very large bucket: the in-switch variant's copy-in / copy-out passes lose to NCCL's
+                # in-place NVLS all_reduce above ~128 MB (8 x B200: 256 MB 895 vs 717 us) - which IS the reference path here
+                dist.all_reduce(g, group=self.group)
+                return
             native._C.allreduce_fused_cuda(
                 self.symm.buffers, g.data_ptr(), b.numel, b.chunks.data_ptr(), b.n_chunks, b.T, e, m, self.rounding,
                 bool(cfg.use_aps), bool(cfg.use_kahan), self.algo_for(b) | _PROTO, bool(cfg.prequantize), self.wire,
