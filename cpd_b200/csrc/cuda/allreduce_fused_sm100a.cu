@@ -316,11 +316,18 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
       // all W peers' vectors requested before the first use
       for (int v4 = (w & 3) * kArThreads + threadIdx.x; v4 < (ck.len >> 2); v4 += 4 * kArThreads) {
         const long long e0 = ck.start + 4 * v4;
-        uint4 in[kArMaxW];
+        // The fold below indexes the peers' vectors with a run-time rank, so `in` lives in local memory.  Loading straight
+        // into it made the compiler emit LDG -> STL pairs through ONE register (the asm loads clobber memory, so each
+        // local store had to precede the next load): 8 SERIALISED ~2 us peer round trips (fold 16 us at W = 8 against 3.7 us
+        // at W = 2, profiles/allreduce_r2t2_*).  Land all W loads in distinct registers first, spill afterwards.
+        uint4 in[kArMaxW], landed[kArMaxW];
 #pragma unroll
         for (int r = 0; r < kArMaxW; ++r)
-          if (r < W) in[r] = p.weak_loads ? *reinterpret_cast<const uint4*>(p.data[r] + par * p.cap_bytes + e0 * 4)
-                                          : ld_sys_u4(p.data[r] + par * p.cap_bytes + e0 * 4);
+          if (r < W) landed[r] = p.weak_loads ? *reinterpret_cast<const uint4*>(p.data[r] + par * p.cap_bytes + e0 * 4)
+                                              : ld_sys_u4(p.data[r] + par * p.cap_bytes + e0 * 4);
+#pragma unroll
+        for (int r = 0; r < kArMaxW; ++r)
+          if (r < W) in[r] = landed[r];
         float s4[4] = {0.f, 0.f, 0.f, 0.f}, c4[4] = {0.f, 0.f, 0.f, 0.f};
         // rolled on purpose (the peers' vectors sit in a small local array): unrolling over 8 ranks only multiplies the code
 #pragma unroll 1
@@ -524,10 +531,16 @@ allreduce_fused_kernel(const ArParams p, const F fmt) {
         granule_decode<WIRE>(fmt, sum, s);
       } else {
       if (WIRE <= 16) {
+        // all W peer loads land in distinct registers BEFORE anything is spilled to the run-time indexed `in` (see the
+        // raw variant above: loading into `in` directly serialised the W NVLink round trips)
+        Granule<WIRE> landed[kPre];
 #pragma unroll
         for (int r = 0; r < kPre; ++r)
-          if (r < W) in[r] = p.weak_loads ? granule_load_weak<WIRE>(p.data[r] + par * p.cap_bytes, e0)
-                                          : granule_load_sys<WIRE>(p.data[r] + par * p.cap_bytes, e0);
+          if (r < W) landed[r] = p.weak_loads ? granule_load_weak<WIRE>(p.data[r] + par * p.cap_bytes, e0)
+                                              : granule_load_sys<WIRE>(p.data[r] + par * p.cap_bytes, e0);
+#pragma unroll
+        for (int r = 0; r < kPre; ++r)
+          if (r < W) in[r] = landed[r];
       }
       if (first && WIRE <= 16) {
         unsigned acc = 0u;
