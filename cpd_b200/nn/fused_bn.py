@@ -21,7 +21,7 @@ import os
 from ..ops import native
 
 # 1-bit ReLU mask for the backward pass instead of re-reading y (CPD_B200_BN_MASK=0 switches it off)
-_USE_MASK = os.environ.get("CPD_B200_BN_MASK", "0") == "1"
+_USE_MASK = os.environ.get("CPD_B200_BN_MASK", "1") == "1"
 
 
 class _BNActFn(torch.autograd.Function):
