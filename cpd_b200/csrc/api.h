@@ -100,6 +100,7 @@ struct StageDesc {
   long long base;          // element offset added to every address (flips start from the far end)
   int mode;                // 0 = GATHER (strided, k split in three), 1 = IM2COL
   int rows_fast;           // 1: the source is contiguous along the output ROW index (read r-fast), 0: along k
+  int vec4;                // set by the launcher: 4 consecutive fast-dimension elements are one aligned 16-byte load
   // GATHER: address = base + r * s_row + k1 * s1 + k2 * s2 + k3 * s3,  k = (k1 * n2 + k2) * n3 + k3
   long long s_row, s1, s2, s3;
   int n2, n3;

@@ -91,6 +91,25 @@ __device__ __forceinline__ float stage_fetch(const StageDesc& d, const StageTabs
   return d.src[t.ra[rr] + t.ca[kk] + (long long)ih * d.sh + (long long)iw * d.sw];
 }
 
+// Four consecutive elements along the source-contiguous ("fast") dimension in ONE 16-byte load (desc.vec4, decided on the
+// host: unit stride along that dimension, every other stride / offset / extent a multiple of 4, 16-byte aligned base).
+// The four share their spatial coordinates (same filter tap, channels c..c+3; or same pixel), so one bounds test serves.
+__device__ __forceinline__ float4 stage_fetch4(const StageDesc& d, const StageTabs& t, int rr, int kk) {
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (d.mode == 0) {
+    if (t.rh[rr] == kOut || t.ch[kk] == kOut) return zero;
+    return *reinterpret_cast<const float4*>(d.src + t.ra[rr] + t.ca[kk]);
+  }
+  int ih = t.rh[rr] + t.ch[kk], iw = t.rw[rr] + t.cw[kk];
+  if (ih < 0 || iw < 0) return zero;
+  if (d.in_dil > 1) {
+    if (ih % d.in_dil || iw % d.in_dil) return zero;
+    ih /= d.in_dil; iw /= d.in_dil;
+  }
+  if (ih >= d.H || iw >= d.W) return zero;
+  return *reinterpret_cast<const float4*>(d.src + t.ra[rr] + t.ca[kk] + (long long)ih * d.sh + (long long)iw * d.sw);
+}
+
 // 8 consecutive k of one row -> operand dtype, one vector store
 template <int OP>
 __device__ __forceinline__ void stage_store8(void* dst_row, int k, const float (&v)[8]) {
@@ -155,12 +174,29 @@ operand_stage_kernel(const StagePair sp) {
     }
     __syncthreads();
     // load phase: the source-contiguous dimension runs across the threads of a warp
+    if (d.vec4) {
+      // 16 lanes x 16 B cover the 64 fast indices of one slow index: 4 elements per load instead of 1 (the scalar loop
+      // was issue-bound: ~30 instructions per element, ncu r2t4_prof_operand_stage_kernel)
+#pragma unroll
+      for (int i = 0; i < kTile * kTile / 4 / kStageThreads; ++i) {
+        const int lin = i * kStageThreads + threadIdx.x;
+        const int f0 = (lin % (kTile / 4)) * 4, slow = lin / (kTile / 4);
+        if (d.rows_fast) {
+          const float4 v = stage_fetch4(d, tabs, f0, slow);
+          tile[f0][slow] = v.x; tile[f0 + 1][slow] = v.y; tile[f0 + 2][slow] = v.z; tile[f0 + 3][slow] = v.w;
+        } else {
+          const float4 v = stage_fetch4(d, tabs, slow, f0);
+          tile[slow][f0] = v.x; tile[slow][f0 + 1] = v.y; tile[slow][f0 + 2] = v.z; tile[slow][f0 + 3] = v.w;
+        }
+      }
+    } else {
 #pragma unroll 4
-    for (int i = 0; i < kTile * kTile / kStageThreads; ++i) {
-      const int lin = i * kStageThreads + threadIdx.x;
-      const int fast = lin % kTile, slow = lin / kTile;
-      const int rr = d.rows_fast ? fast : slow, kk = d.rows_fast ? slow : fast;
-      tile[rr][kk] = stage_fetch(d, tabs, rr, kk);
+      for (int i = 0; i < kTile * kTile / kStageThreads; ++i) {
+        const int lin = i * kStageThreads + threadIdx.x;
+        const int fast = lin % kTile, slow = lin / kTile;
+        const int rr = d.rows_fast ? fast : slow, kk = d.rows_fast ? slow : fast;
+        tile[rr][kk] = stage_fetch(d, tabs, rr, kk);
+      }
     }
     __syncthreads();
     // store phase: 8 consecutive k per thread, rows across the rest
@@ -202,6 +238,25 @@ colsum_quantize_kernel(const float* __restrict__ x, long long rows, int cols, lo
 
 }  // namespace
 
+// Can groups of 4 along the source-contiguous dimension be fetched with one aligned 16-byte load?
+static bool stage_can_vec4(const StageDesc& d, long long R, long long K) {
+  auto m4 = [](long long v) { return (v & 3) == 0; };
+  if (reinterpret_cast<uintptr_t>(d.src) & 15u) return false;
+  if (!m4(d.base)) return false;
+  if (d.mode == 0) {
+    if (d.rows_fast) {                                   // rows contiguous: r, r+1, r+2, r+3 at one k
+      if (d.s_row != 1 || !m4(R)) return false;
+      return m4(d.s1) && (d.n2 == 1 || m4(d.s2)) && (d.n3 == 1 || m4(d.s3));
+    }
+    if (!m4(K) || !m4(d.s_row)) return false;
+    if (d.n2 == 1 && d.n3 == 1) return d.s1 == 1;        // plain 2-D, K contiguous
+    return d.s3 == 1 && m4(d.n3) && m4(d.s1) && m4(d.s2);    // 3-level gather with a contiguous innermost level
+  }
+  // IM2COL: channels contiguous (channels_last) and they are the fast dimension of this staging
+  if (d.sc != 1 || !m4(d.C) || !m4(d.sb) || !m4(d.sh) || !m4(d.sw)) return false;
+  return (d.rows_fast != 0) == (d.taps_are_rows != 0);
+}
+
 int operand_stage2_cuda(const StageDesc* descs, void* const* dsts, const long long* R, const long long* K, const long long* Kp,
                         int n, int operand_mode, cudaStream_t st) {
   if (n < 1 || n > 2) return -3;
@@ -212,6 +267,7 @@ int operand_stage2_cuda(const StageDesc* descs, void* const* dsts, const long lo
     if (R[i] <= 0 || K[i] <= 0 || R[i] >= (1LL << 31) || K[i] >= (1LL << 31)) return -4;      // 32-bit index arithmetic
     if (Kp[i] < K[i] || Kp[i] % 8) return -1;                       // rows are written in 8-element vectors
     sp.d[i] = descs[i]; sp.dst[i] = dsts[i]; sp.R[i] = R[i]; sp.K[i] = K[i]; sp.Kp[i] = Kp[i];
+    sp.d[i].vec4 = stage_can_vec4(descs[i], R[i], K[i]) ? 1 : 0;
     n_tiles += ((R[i] + kTile - 1) / kTile) * ((Kp[i] + kTile - 1) / kTile);
   }
   const long long cap = (long long)device_sm_count(-1) * 8;
