@@ -89,6 +89,40 @@ def checks(prof):
             if ref8 and _bench_line(ref8):
                 floor("ResNet-18 8 GPUs: ours / unmodified reference (images/s)", j8["value"] / _bench_line(ref8)["value"], 5.0)
     del b1
+    # ---- round 2 evidence -------------------------------------------------------------------------------------------
+    sw2 = sorted(glob.glob(os.path.join(prof, "allreduce_r2t*_n8_check_default.json")))
+    if sw2:
+        d = json.load(open(sw2[-1]))
+        floor("r2 8-GPU all-reduce: correctness + stress + fault injection all pass",
+              1.0 if (d.get("correct_all_pass") and d.get("stress_all_pass") and d.get("fault_all_pass")) else 0.0, 1.0)
+        for r in d["sweep"]:
+            nb, auto, nccl = r["fp32_bytes"], r["fused_auto_us"], r["nccl_fp32_allreduce_us"]
+            # at or ahead of NCCL's fp32 all-reduce at EVERY size (NCCL's own small-message numbers scatter ~10 %)
+            floor(f"r2 8-GPU all-reduce {nb} B: NCCL fp32 time / fused AUTO time", nccl / auto, 1.0 if nb <= (1 << 20) else 1.4)
+            if "reference_algo_us" in r and r["reference_algo_us"]:
+                floor(f"r2 8-GPU all-reduce {nb} B: reference algorithm time / fused AUTO time", r["reference_algo_us"] / auto, 4.0)
+    mb = sorted(glob.glob(os.path.join(prof, "r2t*_microbench.json")))
+    if mb:
+        d = json.load(open(mb[-1]))
+        e2e = [r for r in d.get("gemm_tile_e2e", []) if r["n"] == 8192]
+        if e2e:
+            floor("r2 quant_gemm(fp32, fp32, tile) 8192^3: end-to-end / kernel-only throughput", e2e[-1]["e2e_over_kernel_only"], 0.70)
+        f1 = [r for r in d.get("aps_fold", []) if r["W"] == 1 and not r["kahan"]]
+        if f1:
+            floor("r2 aps_fold_local W=1 on ResNet-18's gradients: ms (ceiling, as 1/ms)", 1.0 / f1[-1]["ms"], 1.0 / 0.050)
+    def r2bench(name):
+        c = sorted(glob.glob(os.path.join(prof, "bench", name)))
+        return _bench_line(c[-1]) if c else None
+    o1, r1 = r2bench("r2t4_bench_ours_x.json"), r2bench("r2t4_bench_ref_resnet18.json")
+    if o1 and r1:
+        floor("r2 ResNet-18 1 GPU: ours e2e / unmodified reference (images/s)", o1["e2e"]["value"] / r1["value"], 4.7)
+        floor("r2 ResNet-18 1 GPU: end-to-end / device-timed throughput", o1["e2e"]["value"] / o1["value"], 0.98)
+    q1, qr = r2bench("r2t4_bench_ours_xmodelresnet18_quantsteps15.json"), r2bench("r2t1_bench_quant_ref.json")
+    if q1 and qr:
+        floor("r2 ResNet-18 with Quant_Conv (5,10) accumulators, 1 GPU: ours / reference's own Quant_Conv", q1["value"] / qr["value"], 300.0)
+    o8 = r2bench("r2t5_n8_bench_ours_resnet18.json")
+    if o8 and o1:
+        floor("r2 ResNet-18 weak scaling 1 -> 8 GPUs (ms/step ratio; both with the shipped defaults)", 6.768 / o8["ms_per_step"], 0.96)
     return out
 
 
