@@ -115,16 +115,18 @@ bn_stats_kernel(const float* __restrict__ x, long long M, int C, long long rows_
   const bool cok = c0 < C;
   const float4 sh = cok ? ld4(running_mean + c0) : make_float4(0.f, 0.f, 0.f, 0.f);       // shift of the shifted-data sums
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-  const long long r0 = (long long)blockIdx.y * rows_per_slab;
-  const long long r1 = r0 + rows_per_slab < M ? r0 + rows_per_slab : M;
+  // Rows are dealt to the grid ROUND-ROBIN in groups of rows_par (not one contiguous slab per CTA): at any moment the
+  // whole grid reads one compact window of the tensor that moves forward - the access pattern of the apply kernels,
+  // which stream at 6.2 TB/s where per-CTA slabs (592 concurrent streams) reached 3.2 TB/s (ncu r2t4_prof_bn_stats_kernel).
+  (void)rows_per_slab;
+  const long long step = (long long)gridDim.y * rows_par;
   if (cok) {
-    long long r = r0 + ty;
-    // 8 independent 16-byte loads in flight per thread: ncu showed the 4-deep version latency-bound (long-scoreboard
-    // stalls 22.8 per issue, 3.2 TB/s = 0.49 of the HBM copy rate on the 134 MB layer)
-    for (; r + 7LL * rows_par < r1; r += 8LL * rows_par) {
+    long long r = (long long)blockIdx.y * rows_par + ty;
+    // 8 independent 16-byte loads in flight per thread
+    for (; r + 7LL * step < M; r += 8LL * step) {
       float4 v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = ld4(x + (r + (long long)j * rows_par) * C + c0);
+      for (int j = 0; j < 8; ++j) v[j] = ld4(x + (r + (long long)j * step) * C + c0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float a = v[j].x - sh.x, b = v[j].y - sh.y, c = v[j].z - sh.z, d = v[j].w - sh.w;
@@ -132,7 +134,7 @@ bn_stats_kernel(const float* __restrict__ x, long long M, int C, long long rows_
         q.x += a * a; q.y += b * b; q.z += c * c; q.w += d * d;
       }
     }
-    for (; r < r1; r += rows_par) {
+    for (; r < M; r += step) {
       const float4 v = ld4(x + r * C + c0);
       const float a = v.x - sh.x, b = v.y - sh.y, c = v.z - sh.z, d = v.w - sh.w;
       s.x += a; s.y += b; s.z += c; s.w += d;
@@ -242,18 +244,18 @@ bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ y, c
   const float4 mu = cok ? ld4(mean + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 rs = cok ? ld4(rstd + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-  const long long r0 = (long long)blockIdx.y * rows_per_slab;
-  const long long r1 = r0 + rows_per_slab < M ? r0 + rows_per_slab : M;
+  (void)rows_per_slab;
+  const long long step = (long long)gridDim.y * rows_par;      // rows dealt round-robin to the grid (see bn_stats_kernel)
   if (cok) {
-    // 4 rows x (dy, x, y) = up to 12 independent 16-byte loads in flight per thread
-    for (long long r = r0 + ty; r < r1; r += 4LL * rows_par) {
+    // 4 rows x (dy, x, mask | y) = up to 12 independent loads in flight per thread
+    for (long long r = (long long)blockIdx.y * rows_par + ty; r < M; r += 4LL * step) {
       float4 g[4], xv[4], yv[4];
       unsigned mb[4];
       bool ok[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const long long rj = r + (long long)j * rows_par;
-        ok[j] = rj < r1;
+        const long long rj = r + (long long)j * step;
+        ok[j] = rj < M;
         const long long a = (ok[j] ? rj : r) * C + c0;
         g[j] = ld4(dy + a);
         xv[j] = ld4(x + a);
