@@ -12,7 +12,13 @@
 // only ONE cast pair per output element per K-slice runs on the CUDA cores, overlapped with
 // the next slice's MMAs through a double-buffered TMEM accumulator.
 //
-// Warp roles (640 threads, 1 CTA / SM, one 128x128 output tile per CTA):
+// PERSISTENT: the grid is min(#tiles, #SMs) CTAs and every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
+// (tile = (split, n-tile, m-tile), m fastest so that neighbouring CTAs share the B tile in L2).  Barrier initialisation,
+// TMEM allocation and the tensor-map prefetch are paid once per CTA instead of once per tile - for the convolution shapes
+// (K = 576: nine K-blocks per tile) that prologue used to cost more than the tile's MMAs - and the three roles keep
+// RUNNING stage / phase counters across tiles, so the TMA ring and the two TMEM accumulator stages stay full over tile
+// boundaries: the last slice's requant + store of tile i overlaps the first MMAs of tile i + 1.
+// Warp roles (640 threads, 1 CTA / SM, 128x128 output tiles):
 //   warp 0      TMA producer   : cp.async.bulk.tensor 2D loads of A and B tiles, 4-stage mbarrier ring
 //   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (M128 x N128 x 32 B of K per
 //                                instruction), tcgen05.commit frees smem stages / publishes TMEM stages
@@ -63,7 +69,7 @@ template <int KIND, class F, bool KAHAN>
 __global__ void __launch_bounds__(tc::NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     float* __restrict__ C, const float* __restrict__ bias, int M, int N, int K, int elem_bytes,
-                    int kblocks_per_slice, uint32_t idesc, F fmt, int kblocks_per_split) {
+                    int kblocks_per_slice, uint32_t idesc, F fmt, int kblocks_per_split, int tiles_m, int tiles_n, int splits) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -72,14 +78,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   Barriers* bars = reinterpret_cast<Barriers*>(smem + NUM_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
   const int k_elems_per_block = STAGE_ROW_BYTES / elem_bytes;
   const int total_kblocks = (K + k_elems_per_block - 1) / k_elems_per_block;
-  // split-K: this CTA owns K-blocks [kb0, kb0 + num_kblocks) and writes its own fp32 partial matrix
-  const int kb0 = blockIdx.z * kblocks_per_split;
-  const int num_kblocks = max(0, min(total_kblocks - kb0, kblocks_per_split));
-  const int num_slices = (num_kblocks + kblocks_per_slice - 1) / kblocks_per_slice;
-  C += (long long)blockIdx.z * M * N;
+  const int num_tiles = tiles_m * tiles_n * splits;
+  float* const C_base = C;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -96,45 +98,62 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
+  // tile -> (split z, n-tile, m-tile) and the split's K-block range
+#define CPD_TILE_COORDS(t)                                                                          \
+  const int tm_ = (t) % tiles_m, tn_ = ((t) / tiles_m) % tiles_n, tz_ = (t) / (tiles_m * tiles_n);   \
+  const int m0 = tm_ * BLOCK_M, n0 = tn_ * BLOCK_N;                                                 \
+  const int kb0 = tz_ * kblocks_per_split;                                                          \
+  const int num_kblocks = max(0, min(total_kblocks - kb0, kblocks_per_split));                      \
+  const int num_slices = (num_kblocks + kblocks_per_slice - 1) / kblocks_per_slice;                 \
+  (void)m0; (void)n0; (void)kb0; (void)num_slices;
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kblocks; ++kb) {
-        const int s = kb % NUM_STAGES;
-        const uint32_t ph = (kb / NUM_STAGES) & 1;
-        mbar_wait(&bars->empty[s], ph ^ 1);
-        mbar_expect_tx(&bars->full[s], A_STAGE_BYTES + B_STAGE_BYTES);
-        tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, &bars->full[s], (kb0 + kb) * k_elems_per_block, m0);
-        tma_load_2d(smem_b + s * B_STAGE_BYTES, &tmap_b, &bars->full[s], (kb0 + kb) * k_elems_per_block, n0);
+      uint32_t it = 0;                                   // running K-block count: smem stage = it % NUM_STAGES
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        CPD_TILE_COORDS(t)
+        for (int kb = 0; kb < num_kblocks; ++kb, ++it) {
+          const int s = it % NUM_STAGES;
+          const uint32_t ph = (it / NUM_STAGES) & 1;
+          mbar_wait(&bars->empty[s], ph ^ 1);
+          mbar_expect_tx(&bars->full[s], A_STAGE_BYTES + B_STAGE_BYTES);
+          tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, &bars->full[s], (kb0 + kb) * k_elems_per_block, m0);
+          tma_load_2d(smem_b + s * B_STAGE_BYTES, &tmap_b, &bars->full[s], (kb0 + kb) * k_elems_per_block, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int kb = 0;
-      for (int sl = 0; sl < num_slices; ++sl) {
-        const int acc = sl % NUM_ACC;
-        const uint32_t acc_ph = (sl / NUM_ACC) & 1;
-        mbar_wait(&bars->tmem_empty[acc], acc_ph ^ 1);
-        tc_fence_after();
-        const uint32_t d_addr = tmem_base + acc * BLOCK_N;
-        const int kb_end = min(num_kblocks, kb + kblocks_per_slice);
-        bool first = true;
-        for (; kb < kb_end; ++kb) {
-          const int s = kb % NUM_STAGES;
-          const uint32_t ph = (kb / NUM_STAGES) & 1;
-          mbar_wait(&bars->full[s], ph);
+      uint32_t it = 0, sl_run = 0;                       // running K-block / K-slice counts across tiles
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        CPD_TILE_COORDS(t)
+        int kb = 0;
+        for (int sl = 0; sl < num_slices; ++sl, ++sl_run) {
+          const int acc = sl_run % NUM_ACC;
+          const uint32_t acc_ph = (sl_run / NUM_ACC) & 1;
+          mbar_wait(&bars->tmem_empty[acc], acc_ph ^ 1);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
-          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
+          const uint32_t d_addr = tmem_base + acc * BLOCK_N;
+          const int kb_end = min(num_kblocks, kb + kblocks_per_slice);
+          bool first = true;
+          for (; kb < kb_end; ++kb, ++it) {
+            const int s = it % NUM_STAGES;
+            const uint32_t ph = (it / NUM_STAGES) & 1;
+            mbar_wait(&bars->full[s], ph);
+            tc_fence_after();
+            const uint64_t adesc = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
+            const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
 #pragma unroll
-          for (int k = 0; k < STAGE_ROW_BYTES / 32; ++k) {          // 32 bytes of K per instruction
-            umma<KIND>(d_addr, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
-            first = false;
+            for (int k = 0; k < STAGE_ROW_BYTES / 32; ++k) {          // 32 bytes of K per instruction
+              umma<KIND>(d_addr, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+              first = false;
+            }
+            umma_commit(&bars->empty[s]);                              // smem stage reusable once these MMAs retire
           }
-          umma_commit(&bars->empty[s]);                              // smem stage reusable once these MMAs retire
+          umma_commit(&bars->tmem_full[acc]);                          // slice accumulator complete
         }
-        umma_commit(&bars->tmem_full[acc]);                          // slice accumulator complete
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -143,56 +162,62 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int quarter = warp & 3;              // TMEM lane quarter this warp may touch
     const int cg = ew >> 2;                    // which 32 columns
     const int row = quarter * 32 + lane;       // accumulator row == TMEM lane
-    float s[EPI_COLS], c[KAHAN ? EPI_COLS : 1];
+    uint32_t sl_run = 0;                       // running K-slice count across tiles (TMEM stage / phase)
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      CPD_TILE_COORDS(t)
+      float* Ct = C_base + (long long)tz_ * M * N;                     // split-K: this split's partial matrix
+      float s[EPI_COLS], c[KAHAN ? EPI_COLS : 1];
 #pragma unroll
-    for (int j = 0; j < EPI_COLS; ++j) s[j] = 0.f;
-    if (KAHAN) {
+      for (int j = 0; j < EPI_COLS; ++j) s[j] = 0.f;
+      if (KAHAN) {
 #pragma unroll
-      for (int j = 0; j < EPI_COLS; ++j) c[KAHAN ? j : 0] = 0.f;
-    }
-    for (int sl = 0; sl < num_slices; ++sl) {
-      const int acc = sl % NUM_ACC;
-      const uint32_t acc_ph = (sl / NUM_ACC) & 1;
-      mbar_wait(&bars->tmem_full[acc], acc_ph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + cg * EPI_COLS;
-      uint32_t v[32];
-      tmem_ld_32x32(taddr, v);
-      tmem_ld_wait();
-      // the TMEM stage is free as soon as the values are in registers: release it before the casts
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);            // 16 warp arrivals free the TMEM stage
-#pragma unroll
-      for (int j = 0; j < EPI_COLS; ++j) {
-        const float p = fmt.q(__uint_as_float(v[j]));
-        if (KAHAN) fold_kahan(fmt, s[j], c[KAHAN ? j : 0], p);
-        else fold_plain(fmt, s[j], p);
+        for (int j = 0; j < EPI_COLS; ++j) c[KAHAN ? j : 0] = 0.f;
       }
-    }
-    // final store (+ bias): thread owns 32 contiguous floats of one row
-    const int gm = m0 + row;
-    const int gn = n0 + cg * EPI_COLS;
-    if (gm < M && gn < N) {
-      float* crow = C + (long long)gm * N + gn;
-      const int ncols = min(EPI_COLS, N - gn);
-      if (ncols == EPI_COLS && (N & 3) == 0) {
+      for (int sl = 0; sl < num_slices; ++sl, ++sl_run) {
+        const int acc = sl_run % NUM_ACC;
+        const uint32_t acc_ph = (sl_run / NUM_ACC) & 1;
+        mbar_wait(&bars->tmem_full[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + cg * EPI_COLS;
+        uint32_t v[32];
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        // the TMEM stage is free as soon as the values are in registers: release it before the casts
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);            // 16 warp arrivals free the TMEM stage
 #pragma unroll
-        for (int j = 0; j < EPI_COLS; j += 4) {
-          float4 o = make_float4(s[j], s[j + 1], s[j + 2], s[j + 3]);
-          if (bias) {
-            const float4 bb = *reinterpret_cast<const float4*>(bias + gn + j);
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-          }
-          *reinterpret_cast<float4*>(crow + j) = o;
+        for (int j = 0; j < EPI_COLS; ++j) {
+          const float p = fmt.q(__uint_as_float(v[j]));
+          if (KAHAN) fold_kahan(fmt, s[j], c[KAHAN ? j : 0], p);
+          else fold_plain(fmt, s[j], p);
         }
-      } else {
+      }
+      // final store (+ bias): thread owns 32 contiguous floats of one row
+      const int gm = m0 + row;
+      const int gn = n0 + cg * EPI_COLS;
+      if (gm < M && gn < N) {
+        float* crow = Ct + (long long)gm * N + gn;
+        const int ncols = min(EPI_COLS, N - gn);
+        if (ncols == EPI_COLS && (N & 3) == 0) {
 #pragma unroll
-        for (int j = 0; j < EPI_COLS; ++j)
-          if (j < ncols) crow[j] = s[j] + (bias ? bias[gn + j] : 0.f);
+          for (int j = 0; j < EPI_COLS; j += 4) {
+            float4 o = make_float4(s[j], s[j + 1], s[j + 2], s[j + 3]);
+            if (bias) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias + gn + j);
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            *reinterpret_cast<float4*>(crow + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < EPI_COLS; ++j)
+            if (j < ncols) crow[j] = s[j] + (bias ? bias[gn + j] : 0.f);
+        }
       }
     }
   }
+#undef CPD_TILE_COORDS
 
   tc_fence_before();
   __syncthreads();
@@ -252,7 +277,10 @@ template <int KIND>
 int launch_kind(const CUtensorMap& ta, const CUtensorMap& tb, float* C, const float* bias, int M, int N, int K, int elem_bytes,
                 int kblocks_per_slice, uint32_t idesc, int e, int m, bool kahan, cudaStream_t st, int splits, int kblocks_per_split,
                 float* workspace) {
-  dim3 grid((N + tc::BLOCK_N - 1) / tc::BLOCK_N, (M + tc::BLOCK_M - 1) / tc::BLOCK_M, splits);
+  const int tiles_n = (N + tc::BLOCK_N - 1) / tc::BLOCK_N, tiles_m = (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
+  const long long num_tiles = (long long)tiles_m * tiles_n * splits;
+  const int sms = device_sm_count(-1);
+  dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));               // persistent: one CTA per SM walks the tiles
   float* out = splits > 1 ? workspace : C;
   const float* kbias = splits > 1 ? nullptr : bias;
   int rc = 0;
@@ -261,11 +289,11 @@ int launch_kind(const CUtensorMap& ta, const CUtensorMap& tb, float* C, const fl
     if (kahan) {
       auto kfn = gemm_tcgen05_kernel<KIND, decltype(FMT), true>;
       if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES) != cudaSuccess) rc = -3;
-      else kfn<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(ta, tb, out, kbias, M, N, K, elem_bytes, kblocks_per_slice, idesc, FMT, kblocks_per_split);
+      else kfn<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(ta, tb, out, kbias, M, N, K, elem_bytes, kblocks_per_slice, idesc, FMT, kblocks_per_split, tiles_m, tiles_n, splits);
     } else {
       auto kfn = gemm_tcgen05_kernel<KIND, decltype(FMT), false>;
       if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES) != cudaSuccess) rc = -3;
-      else kfn<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(ta, tb, out, kbias, M, N, K, elem_bytes, kblocks_per_slice, idesc, FMT, kblocks_per_split);
+      else kfn<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(ta, tb, out, kbias, M, N, K, elem_bytes, kblocks_per_slice, idesc, FMT, kblocks_per_split, tiles_m, tiles_n, splits);
     }
     if (rc == 0 && splits > 1) {
       const long long MN = (long long)M * N;
