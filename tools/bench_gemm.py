@@ -35,10 +35,11 @@ def load_reference():
 
 
 def main():
+    quick = "--quick" in sys.argv          # tensor-core GEMM only: three shapes, bf16 operands, three accumulator settings
     hbm, tflops, src = peaks()
-    ref = load_reference()
+    ref = None if quick else load_reference()
     res = {"peaks": {"hbm_gbs": hbm, "bf16_tflops": tflops, "source": src}, "quantize": [], "gemm_exact": [], "gemm_tc": []}
-    for n in (1 << 20, 1 << 24, 1 << 28):
+    for n in (() if quick else (1 << 20, 1 << 24, 1 << 28)):
         x = torch.randn(n, device="cuda")
         out = torch.empty_like(x)
         ms = time_ms(lambda: native.quantize_(x, out, 4, 3))
@@ -49,7 +50,7 @@ def main():
             row.update(ref_ms=round(msr, 4), ref_GBps=round(8 * n / msr / 1e6, 1), speedup=round(msr / ms, 2))
         res["quantize"].append(row)
         del x, out
-    for n in (64, 1024, 4096):
+    for n in (() if quick else (64, 1024, 4096)):
         a, b = torch.randn(n, n, device="cuda"), torch.randn(n, n, device="cuda")
         it = 5 if n <= 1024 else 2
         ms = time_ms(lambda: quant_gemm(a, b, man=3, exp=4, mode="exact"), iters=it, warm=1, flush=False)
@@ -58,15 +59,20 @@ def main():
             msr = time_ms(lambda: ref.quant_gemm(a, b, man=3, exp=4), iters=it, warm=1, flush=False)
             row.update(ref_ms=round(msr, 3), ref_GFLOPs=round(2 * n ** 3 / msr / 1e6, 1), exact_speedup=round(msr / ms, 2))
         res["gemm_exact"].append(row)
-    for (M, N, K) in ((1024, 1024, 1024), (4096, 4096, 4096), (8192, 8192, 8192), (524288, 64, 576), (32768, 256, 2304)):
-        for mode, dt, name in ((native.OPERAND_BF16, torch.bfloat16, "bf16"), (native.OPERAND_E4M3, torch.float8_e4m3fn, "e4m3"),
-                               (native.OPERAND_TF32, torch.float32, "tf32")):
+    shapes = ((4096, 4096, 4096), (8192, 8192, 8192), (524288, 64, 576), (65536, 64, 576), (32768, 256, 2304)) if quick else \
+        ((1024, 1024, 1024), (4096, 4096, 4096), (8192, 8192, 8192), (524288, 64, 576), (32768, 256, 2304))
+    kinds = ((native.OPERAND_BF16, torch.bfloat16, "bf16"), (native.OPERAND_E4M3, torch.float8_e4m3fn, "e4m3"),
+             (native.OPERAND_TF32, torch.float32, "tf32"))
+    for (M, N, K) in shapes:
+        for mode, dt, name in (kinds[:1] if quick else kinds):
             if M * K * (4 if name == "tf32" else 2) > (8 << 30):
                 continue
             a = torch.randn(M, K, device="cuda").to(dt)
             bt = torch.randn(N, K, device="cuda").to(dt)
             out = torch.empty(M, N, device="cuda")
-            for (e, m, kahan, ks) in ((8, 23, False, 0), (5, 10, False, 0), (5, 10, False, 1024), (5, 10, False, 256), (4, 3, False, 128), (5, 2, True, 256)):
+            accs = ((8, 23, False, 0), (5, 10, False, 0), (5, 10, False, 256)) if quick else \
+                ((8, 23, False, 0), (5, 10, False, 0), (5, 10, False, 1024), (5, 10, False, 256), (4, 3, False, 128), (5, 2, True, 256))
+            for (e, m, kahan, ks) in accs:
                 if ks and ks > K:
                     continue
                 for variant, vname in ((native.GEMM_1CTA, "1cta_128x128"), (native.GEMM_2CTA, "2cta_256x256")):
