@@ -77,8 +77,24 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ part, 
   const int c0 = (blockIdx.x * lanes + lane) * 4;
   double4 a = make_double4(0.0, 0.0, 0.0, 0.0), b = a;
   if (c0 < C) {
-    for (int sl = g; sl < slabs; sl += G) {
-      const float4 u = __ldcg(reinterpret_cast<const float4*>(part + ((long long)sl * 2 + 0) * C + c0));     // other SMs wrote these
+    // 8 slabs' partials (16 independent L2 loads) in flight per thread, then added in slab order: the loop is a chain of
+    // L2 round trips otherwise (~37 of them for 592 slabs: the tail of every statistics launch)
+    int sl = g;
+    for (; sl + 7 * G < slabs; sl += 8 * G) {
+      float4 u[8], v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        u[j] = __ldcg(reinterpret_cast<const float4*>(part + ((long long)(sl + j * G) * 2 + 0) * C + c0));     // other SMs wrote these
+        v[j] = __ldcg(reinterpret_cast<const float4*>(part + ((long long)(sl + j * G) * 2 + 1) * C + c0));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a.x += u[j].x; a.y += u[j].y; a.z += u[j].z; a.w += u[j].w;
+        b.x += v[j].x; b.y += v[j].y; b.z += v[j].z; b.w += v[j].w;
+      }
+    }
+    for (; sl < slabs; sl += G) {
+      const float4 u = __ldcg(reinterpret_cast<const float4*>(part + ((long long)sl * 2 + 0) * C + c0));
       const float4 v = __ldcg(reinterpret_cast<const float4*>(part + ((long long)sl * 2 + 1) * C + c0));
       a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
       b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;

@@ -28,3 +28,14 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:8]:
 PY
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05_kernel -s 2 -c 1 -o $OUT/prof_gemm_tcgen05_kernel python tools/ncu_targets.py conv > $OUT/ncu_gemm.log 2>&1; echo "ncu gemm rc=$?"
 python tools/summarize_profiles.py "r2t8" > $OUT/summarize.log 2>&1; grep -E "gpu__time_duration|pipe_tensor_cycles" profiles/ncu/r2t8_prof_gemm_tcgen05_kernel.md | head -3
+timeout 200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum --clock-control none -k regex:bn_ --csv --log-file $OUT/bn_times.csv python tools/ncu_targets.py bn > $OUT/ncu_bn.log 2>&1
+python - <<PY
+import csv
+rows = list(csv.reader(open("$OUT/bn_times.csv", errors="ignore")))
+hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+H = rows[hdr]; kn, mn, mv = H.index("Kernel Name"), H.index("Metric Name"), H.index("Metric Value")
+for r in rows[hdr + 1:][-16:]:
+    if len(r) > mv: print(r[kn][:40], r[mn], r[mv])
+PY
+timeout 300 python bench.py --steps 30 --warmup 5 > $OUT/bench_ours_1.json 2>> $OUT/bench.err; python -c "
+import json; d=json.loads(open('$OUT/bench_ours_1.json').read().strip().splitlines()[-1]); print('ours', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'])"
