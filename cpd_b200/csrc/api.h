@@ -139,16 +139,25 @@ int bn_act_backward_cuda(const float* dy, const float* y, const unsigned* relu_m
 // contiguous range of K-slices into workspace[z] (fp32 [splits, M, N]); a second kernel folds the splits IN ORDER,
 // C = fold_z Q(C (+) part_z) (+ bias): the ordered low-precision fold of CPD applied across K ranges, which gives
 // the skinny weight-gradient GEMMs (reduction over batch x pixels) a grid that fills the machine.
+// conv != nullptr: IMPLICIT-GEMM convolution - A is not a matrix but the NHWC activation tensor itself (already in the
+// operand dtype), read through an im2col-mode TMA descriptor: M = B*OH*OW output positions, K = KH*KW*C in (kh, kw, c)
+// order; lda is ignored.  Needs C % (128 B / element size) == 0.
+struct ConvGeom {
+  int B, H, W, C;               // activation tensor [B, H, W, C], C contiguous
+  int KH, KW, OH, OW;
+  int stride, pad, dil;
+};
 int gemm_tc_cuda(const void* A, const void* B, float* C, int M, int N, int K, int e, int m,
                  bool kahan, int k_slice, int operand_mode, const float* bias, int variant, cudaStream_t st,
-                 long long lda = 0, long long ldb = 0, int splits = 1, float* workspace = nullptr);
+                 long long lda = 0, long long ldb = 0, int splits = 1, float* workspace = nullptr, const ConvGeom* conv = nullptr);
 // MXFP8 operand staging: fp32 [R,K] -> fp8 codes [R,Kp] + UE8M0 per-32 block scales in the tcgen05 scale-factor atom layout
 void mx_quantize_cuda(const float* in, long long ld_in, uint8_t* codes, uint8_t* sf, int R, int K, int Kp, bool e5m2, cudaStream_t st);
 // block-scaled GEMM (tcgen05.mma.kind::mxf8f6f4.block_scale) with per-K-slice accumulator requant
 int gemm_tc_mx_cuda(const uint8_t* codes_a, const uint8_t* sf_a, const uint8_t* codes_b, const uint8_t* sf_b, float* C, int M, int N,
                     int Kp, int e, int m, bool kahan, int k_slice, bool e5m2, const float* bias, cudaStream_t st);
 int gemm_tc2_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, int e, int m, bool kahan, int k_slice,
-                  int operand_mode, const float* bias, cudaStream_t st, long long lda = 0, long long ldb = 0);
+                  int operand_mode, const float* bias, cudaStream_t st, long long lda = 0, long long ldb = 0,
+                  const ConvGeom* conv = nullptr);
 #endif
 
 }  // namespace cpd

@@ -86,7 +86,7 @@ template <int KIND, class ACC, bool KAHAN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc2::NUM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          float* __restrict__ C, const float* __restrict__ bias, int M, int N, int K, int elem_bytes,
-                         int kblocks_per_slice, uint32_t idesc, int tiles_n) {
+                         int kblocks_per_slice, uint32_t idesc, int tiles_n, int num_tiles, tc::ConvA conv) {
   using namespace tc2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -96,11 +96,16 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();           // 0 = leader (issues the MMAs)
-  const int pair = blockIdx.x >> 1;
-  const int tile_m = pair / tiles_n, tile_n = pair % tiles_n;
-  const int m0 = tile_m * PAIR_M + (int)cta_rank * CTA_M;          // this CTA's rows of A / C
-  const int n0 = tile_n * BLOCK_N;
-  const int nb0 = n0 + (int)cta_rank * CTA_BROWS;                   // this CTA's rows of Bt
+  // Persistent: CTA pair p walks output tiles p, p + #pairs, ... with RUNNING smem-stage / TMEM-stage counters, so the
+  // prologue (barriers, TMEM allocation, cluster syncs, pipeline fill) is paid once per pair and tile i's final requant +
+  // store overlaps tile i+1's first MMAs (the TMEM stage is handed back as soon as it is in registers).
+  const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+#define CPD_TILE2_COORDS(t)                                                                          \
+  const int tile_m = (t) / tiles_n, tile_n = (t) % tiles_n;                                          \
+  const int m0 = tile_m * PAIR_M + (int)cta_rank * CTA_M;          /* this CTA's rows of A / C */    \
+  const int n0 = tile_n * BLOCK_N;                                                                   \
+  const int nb0 = n0 + (int)cta_rank * CTA_BROWS;                  /* this CTA's rows of Bt */       \
+  (void)m0; (void)n0; (void)nb0;
   const int k_elems_per_block = STAGE_ROW_BYTES / elem_bytes;
   const int num_kblocks = (K + k_elems_per_block - 1) / k_elems_per_block;
   const int num_slices = (num_kblocks + kblocks_per_slice - 1) / kblocks_per_slice;
@@ -121,30 +126,49 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kblocks; ++kb) {
-        const int s = kb % NUM_STAGES;
-        const uint32_t ph = (kb / NUM_STAGES) & 1;
-        mbar_wait(&bars->empty[s], ph ^ 1);
-        if (cta_rank == 0) mbar_expect_tx(&bars->full[s], 2 * (A_STAGE_BYTES + B_STAGE_BYTES));   // bytes of BOTH CTAs
-        tma_load_2d_2cta(smem_a + s * A_STAGE_BYTES, &tmap_a, &bars->full[s], kb * k_elems_per_block, m0);
-        tma_load_2d_2cta(smem_b + s * B_STAGE_BYTES, &tmap_b, &bars->full[s], kb * k_elems_per_block, nb0);
+      uint32_t it = 0;                                     // running K-block count across tiles
+      for (int t = pair0; t < num_tiles; t += pair_step) {
+        CPD_TILE2_COORDS(t)
+        int cw = 0, ch = 0, cn = 0;                        // implicit GEMM: base pixel of this CTA's first output position
+        if (conv.cblocks) {
+          cn = m0 / conv.OHW;
+          const int rem = m0 - cn * conv.OHW, p = rem / conv.OW;
+          ch = p * conv.stride - conv.pad;
+          cw = (rem - p * conv.OW) * conv.stride - conv.pad;
+        }
+        for (int kb = 0; kb < num_kblocks; ++kb, ++it) {
+          const int s = it % NUM_STAGES;
+          const uint32_t ph = (it / NUM_STAGES) & 1;
+          mbar_wait(&bars->empty[s], ph ^ 1);
+          if (cta_rank == 0) mbar_expect_tx(&bars->full[s], 2 * (A_STAGE_BYTES + B_STAGE_BYTES));   // bytes of BOTH CTAs
+          if (conv.cblocks) {
+            const int tap = kb / conv.cblocks, cb = kb - tap * conv.cblocks;
+            const int r = tap / conv.KW, sx = tap - r * conv.KW;
+            tma_load_im2col_4d_2cta(smem_a + s * A_STAGE_BYTES, &tmap_a, &bars->full[s], cb * k_elems_per_block, cw, ch, cn,
+                                    (uint16_t)(sx * conv.dil), (uint16_t)(r * conv.dil));
+          } else
+          tma_load_2d_2cta(smem_a + s * A_STAGE_BYTES, &tmap_a, &bars->full[s], kb * k_elems_per_block, m0);
+          tma_load_2d_2cta(smem_b + s * B_STAGE_BYTES, &tmap_b, &bars->full[s], kb * k_elems_per_block, nb0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (cta_rank == 0 && lane == 0) {
+      uint32_t it = 0, sl_run = 0;                         // running K-block / K-slice counts across tiles
+      for (int t = pair0; t < num_tiles; t += pair_step) {
       int kb = 0;
-      for (int sl = 0; sl < num_slices; ++sl) {
-        const int acc = sl % NUM_ACC;
-        const uint32_t acc_ph = (sl / NUM_ACC) & 1;
+      for (int sl = 0; sl < num_slices; ++sl, ++sl_run) {
+        const int acc = sl_run % NUM_ACC;
+        const uint32_t acc_ph = (sl_run / NUM_ACC) & 1;
         mbar_wait(&bars->tmem_empty[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_addr = tmem_base + acc * BLOCK_N;
         const int kb_end = min(num_kblocks, kb + kblocks_per_slice);
         bool first = true;
-        for (; kb < kb_end; ++kb) {
-          const int s = kb % NUM_STAGES;
-          const uint32_t ph = (kb / NUM_STAGES) & 1;
+        for (; kb < kb_end; ++kb, ++it) {
+          const int s = it % NUM_STAGES;
+          const uint32_t ph = (it / NUM_STAGES) & 1;
           mbar_wait(&bars->full[s], ph);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
@@ -158,6 +182,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         umma_commit_2cta(&bars->tmem_full[acc]);         // slice accumulator complete, in BOTH CTAs
       }
+      }
     }
   } else if (warp >= EPI_WARP0) {
     // ===================== requant epilogue =====================
@@ -167,6 +192,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int row = quarter * 32 + lane;
     const uint32_t leader_tmem_empty0 = mapa_shared(smem_u32(&bars->tmem_empty[0]), 0);
     const uint32_t leader_tmem_empty1 = mapa_shared(smem_u32(&bars->tmem_empty[1]), 0);
+    uint32_t sl_run = 0;                                 // running K-slice count across tiles (TMEM stage / phase)
+    for (int t = pair0; t < num_tiles; t += pair_step) {
+    CPD_TILE2_COORDS(t)
     uint32_t s2[EPI_COLS / 2], c2[KAHAN ? EPI_COLS / 2 : 1];
 #pragma unroll
     for (int j = 0; j < EPI_COLS / 2; ++j) s2[j] = 0u;
@@ -174,9 +202,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
       for (int j = 0; j < EPI_COLS / 2; ++j) c2[KAHAN ? j : 0] = 0u;
     }
-    for (int sl = 0; sl < num_slices; ++sl) {
-      const int acc = sl % NUM_ACC;
-      const uint32_t acc_ph = (sl / NUM_ACC) & 1;
+    for (int sl = 0; sl < num_slices; ++sl, ++sl_run) {
+      const int acc = sl_run % NUM_ACC;
+      const uint32_t acc_ph = (sl_run / NUM_ACC) & 1;
       mbar_wait(&bars->tmem_full[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + cg * EPI_COLS;
@@ -235,7 +263,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
       }
     }
+    }
   }
+#undef CPD_TILE2_COORDS
 
   tc_fence_before();
   cluster_sync_all();                                    // the peer may still be reading our smem / signalling our barriers
@@ -246,6 +276,11 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 }
 
 // ---- host side ---------------------------------------------------------------------------------
+// gemm_tcgen05_sm100a.cu
+bool make_tmap_im2col(CUtensorMap* tm, const void* base, const ConvGeom& g, int elem_bytes, CUtensorMapDataType dt, int box_pixels);
+bool conv_geom_ok(const ConvGeom& g, int elem_bytes, int M, int K);
+tc::ConvA conv_device_geom(const ConvGeom* g, int elem_bytes);
+
 namespace {
 
 using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -270,28 +305,46 @@ bool make_tmap2(CUtensorMap* tm, const void* base, int rows, int K, long long ld
 
 template <int KIND, class ACC>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, float* C, const float* bias, int M, int N, int K, int elem_bytes,
-            int kblocks_per_slice, uint32_t idesc, bool kahan, cudaStream_t st) {
+            int kblocks_per_slice, uint32_t idesc, bool kahan, cudaStream_t st, const tc::ConvA& conv) {
   const int tiles_m = (M + tc2::PAIR_M - 1) / tc2::PAIR_M, tiles_n = (N + tc2::BLOCK_N - 1) / tc2::BLOCK_N;
-  const dim3 grid(2 * tiles_m * tiles_n);
+  const int num_tiles = tiles_m * tiles_n;
+  static int max_pairs = 0;                                // co-resident CTA pairs (clusters of 2; a GPC with an odd SM count loses one)
+  if (!max_pairs) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    max_pairs = sms > 1 ? sms / 2 : 1;
+    auto probe = gemm_tcgen05_2cta_kernel<KIND, ACC, false>;
+    if (cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * max_pairs); cfg.blockDim = dim3(tc2::NUM_THREADS); cfg.dynamicSmemBytes = tc2::SMEM_BYTES;
+      cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, probe, &cfg) == cudaSuccess && n > 0 && n < max_pairs) max_pairs = n;
+    }
+    (void)cudaGetLastError();
+  }
+  const dim3 grid(2 * (num_tiles < max_pairs ? num_tiles : max_pairs));
   if (kahan) {
     auto kfn = gemm_tcgen05_2cta_kernel<KIND, ACC, true>;
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES) != cudaSuccess) return -3;
-    kfn<<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, tiles_n);
+    kfn<<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, tiles_n, num_tiles, conv);
   } else {
     auto kfn = gemm_tcgen05_2cta_kernel<KIND, ACC, false>;
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES) != cudaSuccess) return -3;
-    kfn<<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, tiles_n);
+    kfn<<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, tiles_n, num_tiles, conv);
   }
   return 0;
 }
 
 template <int KIND>
 int launch2_fmt(const CUtensorMap& ta, const CUtensorMap& tb, float* C, const float* bias, int M, int N, int K, int elem_bytes,
-                int kbs, uint32_t idesc, int e, int m, bool kahan, cudaStream_t st) {
-  if (e == 5 && m == 10) return launch2<KIND, tc2::AccF16>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, kahan, st);
-  if (e == 8 && m == 7) return launch2<KIND, tc2::AccBF16>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, kahan, st);
-  if (e == 4 && m == 3) return launch2<KIND, tc2::AccE4M3>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, kahan, st);
-  if (e == 5 && m == 2) return launch2<KIND, tc2::AccE5M2>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, kahan, st);
+                int kbs, uint32_t idesc, int e, int m, bool kahan, cudaStream_t st, const tc::ConvA& conv) {
+  if (e == 5 && m == 10) return launch2<KIND, tc2::AccF16>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, kahan, st, conv);
+  if (e == 8 && m == 7) return launch2<KIND, tc2::AccBF16>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, kahan, st, conv);
+  if (e == 4 && m == 3) return launch2<KIND, tc2::AccE4M3>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, kahan, st, conv);
+  if (e == 5 && m == 2) return launch2<KIND, tc2::AccE5M2>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, kahan, st, conv);
   return -5;
 }
 
@@ -299,7 +352,7 @@ int launch2_fmt(const CUtensorMap& ta, const CUtensorMap& tb, float* C, const fl
 
 // Returns 0 on launch, <0 if this kernel does not cover the request (the caller then uses the 1-CTA kernel).
 int gemm_tc2_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, int e, int m, bool kahan, int k_slice,
-                  int operand_mode, const float* bias, cudaStream_t st, long long lda, long long ldb) {
+                  int operand_mode, const float* bias, cudaStream_t st, long long lda, long long ldb, const ConvGeom* conv) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (lda <= 0) lda = K;
   if (ldb <= 0) ldb = K;
@@ -315,18 +368,24 @@ int gemm_tc2_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, 
     case 3: elem_bytes = 1; kind = 2; fmt_code = 1; dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; break;
     default: return -1;
   }
+  if (conv) {
+    if (!conv_geom_ok(*conv, elem_bytes, M, K)) return -7;
+    lda = K;
+  }
   if ((lda * elem_bytes) % 16 != 0 || (ldb * elem_bytes) % 16 != 0) return -2;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt)) & 15u) return -2;
   const int k_elems_per_block = tc::STAGE_ROW_BYTES / elem_bytes;
   int kbs = k_slice <= 0 ? (K + k_elems_per_block - 1) / k_elems_per_block : (k_slice + k_elems_per_block - 1) / k_elems_per_block;
   if (kbs < 1) kbs = 1;
   CUtensorMap ta, tb;
-  if (!make_tmap2(&ta, A, M, K, lda, elem_bytes, dt, tc2::CTA_M) || !make_tmap2(&tb, Bt, N, K, ldb, elem_bytes, dt, tc2::CTA_BROWS)) return -4;
+  if (!(conv ? make_tmap_im2col(&ta, A, *conv, elem_bytes, dt, tc2::CTA_M) : make_tmap2(&ta, A, M, K, lda, elem_bytes, dt, tc2::CTA_M)) ||
+      !make_tmap2(&tb, Bt, N, K, ldb, elem_bytes, dt, tc2::CTA_BROWS)) return -4;
+  const tc::ConvA cgeom = conv_device_geom(conv, elem_bytes);
   const uint32_t idesc = (1u << 4) | (fmt_code << 7) | (fmt_code << 10) | ((uint32_t)(tc2::BLOCK_N >> 3) << 17) |
                          ((uint32_t)(tc2::PAIR_M >> 4) << 24);
-  if (kind == 0) return launch2_fmt<0>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, e, m, kahan, st);
-  if (kind == 1) return launch2_fmt<1>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, e, m, kahan, st);
-  return launch2_fmt<2>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, e, m, kahan, st);
+  if (kind == 0) return launch2_fmt<0>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, e, m, kahan, st, cgeom);
+  if (kind == 1) return launch2_fmt<1>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, e, m, kahan, st, cgeom);
+  return launch2_fmt<2>(ta, tb, C, bias, M, N, K, elem_bytes, kbs, idesc, e, m, kahan, st, cgeom);
 }
 
 }  // namespace cpd

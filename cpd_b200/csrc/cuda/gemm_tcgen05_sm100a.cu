@@ -69,7 +69,8 @@ template <int KIND, class F, bool KAHAN>
 __global__ void __launch_bounds__(tc::NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     float* __restrict__ C, const float* __restrict__ bias, int M, int N, int K, int elem_bytes,
-                    int kblocks_per_slice, uint32_t idesc, F fmt, int kblocks_per_split, int tiles_m, int tiles_n, int splits) {
+                    int kblocks_per_slice, uint32_t idesc, F fmt, int kblocks_per_split, int tiles_m, int tiles_n, int splits,
+                    tc::ConvA conv) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -113,12 +114,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t it = 0;                                   // running K-block count: smem stage = it % NUM_STAGES
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         CPD_TILE_COORDS(t)
+        int cw = 0, ch = 0, cn = 0;                      // implicit GEMM: base pixel of the tile's first output position
+        if (conv.cblocks) {
+          cn = m0 / conv.OHW;
+          const int rem = m0 - cn * conv.OHW, p = rem / conv.OW;
+          ch = p * conv.stride - conv.pad;
+          cw = (rem - p * conv.OW) * conv.stride - conv.pad;
+        }
         for (int kb = 0; kb < num_kblocks; ++kb, ++it) {
           const int s = it % NUM_STAGES;
           const uint32_t ph = (it / NUM_STAGES) & 1;
           mbar_wait(&bars->empty[s], ph ^ 1);
           mbar_expect_tx(&bars->full[s], A_STAGE_BYTES + B_STAGE_BYTES);
-          tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, &bars->full[s], (kb0 + kb) * k_elems_per_block, m0);
+          if (conv.cblocks) {
+            const int tap = (kb0 + kb) / conv.cblocks, cb = (kb0 + kb) - tap * conv.cblocks;
+            const int r = tap / conv.KW, sx = tap - r * conv.KW;
+            tma_load_im2col_4d(smem_a + s * A_STAGE_BYTES, &tmap_a, &bars->full[s], cb * k_elems_per_block, cw, ch, cn,
+                               (uint16_t)(sx * conv.dil), (uint16_t)(r * conv.dil));
+          } else {
+            tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, &bars->full[s], (kb0 + kb) * k_elems_per_block, m0);
+          }
           tma_load_2d(smem_b + s * B_STAGE_BYTES, &tmap_b, &bars->full[s], (kb0 + kb) * k_elems_per_block, n0);
         }
       }
@@ -256,6 +271,55 @@ bool make_tmap(CUtensorMap* tm, const void* base, int rows, int K, long long ld,
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+}  // namespace
+
+// NHWC activation tensor read in im2col mode: one load = box_pixels consecutive output positions x (128 B of channels) of
+// one filter tap; the bounding box [-pad, dim + pad - (K-1)*dil) and the traversal stride make the hardware enumerate
+// exactly the OW x OH output positions of every image, the halo is zero-filled
+bool make_tmap_im2col(CUtensorMap* tm, const void* base, const ConvGeom& g, int elem_bytes, CUtensorMapDataType dt, int box_pixels) {
+  using PFN_encodeIm2col = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static PFN_encodeIm2col enc = nullptr;
+  if (!enc) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+    enc = reinterpret_cast<PFN_encodeIm2col>(p);
+  }
+  cuuint64_t gdim[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+  cuuint64_t gstride[3] = {(cuuint64_t)g.C * elem_bytes, (cuuint64_t)g.W * g.C * elem_bytes, (cuuint64_t)g.H * g.W * g.C * elem_bytes};
+  int lower[2] = {-g.pad, -g.pad};
+  int upper[2] = {g.pad - (g.KW - 1) * g.dil, g.pad - (g.KH - 1) * g.dil};
+  cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
+  return enc(tm, dt, 4, const_cast<void*>(base), gdim, gstride, lower, upper, (cuuint32_t)(tc::STAGE_ROW_BYTES / elem_bytes),
+             (cuuint32_t)box_pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// does the implicit-GEMM path cover this convolution?  (corner / offset ranges of the descriptor, whole channel blocks)
+bool conv_geom_ok(const ConvGeom& g, int elem_bytes, int M, int K) {
+  const int cpb = tc::STAGE_ROW_BYTES / elem_bytes;
+  if (g.C <= 0 || g.C % cpb) return false;
+  if (g.stride < 1 || g.stride > 8 || g.dil < 1 || g.pad < 0 || g.pad > 127) return false;
+  if ((g.KH - 1) * g.dil > 255 || (g.KW - 1) * g.dil > 255) return false;
+  if (g.pad - (g.KW - 1) * g.dil < -128 || g.pad - (g.KH - 1) * g.dil < -128) return false;
+  if (g.OH != (g.H + 2 * g.pad - g.dil * (g.KH - 1) - 1) / g.stride + 1 || g.OW != (g.W + 2 * g.pad - g.dil * (g.KW - 1) - 1) / g.stride + 1) return false;
+  if (g.OH < 1 || g.OW < 1) return false;
+  return (long long)g.B * g.OH * g.OW == M && (long long)g.KH * g.KW * g.C == K;
+}
+
+tc::ConvA conv_device_geom(const ConvGeom* g, int elem_bytes) {
+  tc::ConvA c = {0, 1, 1, 1, 0, 1, 1};
+  if (g) {
+    c.cblocks = g->C / (tc::STAGE_ROW_BYTES / elem_bytes);
+    c.OHW = g->OH * g->OW; c.OW = g->OW; c.stride = g->stride; c.pad = g->pad; c.dil = g->dil; c.KW = g->KW;
+  }
+  return c;
+}
+
+namespace {
+
 // C = fold_z Q(C (+) part_z) (+ bias): ordered low-precision fold of the split-K partials (each already a member of
 // the format: the splits' own last cast), same cast as the GEMM epilogue
 template <class F, bool KAHAN>
@@ -276,7 +340,7 @@ splitk_fold_kernel(const float* __restrict__ parts, int splits, long long MN, in
 template <int KIND>
 int launch_kind(const CUtensorMap& ta, const CUtensorMap& tb, float* C, const float* bias, int M, int N, int K, int elem_bytes,
                 int kblocks_per_slice, uint32_t idesc, int e, int m, bool kahan, cudaStream_t st, int splits, int kblocks_per_split,
-                float* workspace) {
+                float* workspace, const tc::ConvA& conv) {
   const int tiles_n = (N + tc::BLOCK_N - 1) / tc::BLOCK_N, tiles_m = (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
   const long long num_tiles = (long long)tiles_m * tiles_n * splits;
   const int sms = device_sm_count(-1);
@@ -289,11 +353,11 @@ int launch_kind(const CUtensorMap& ta, const CUtensorMap& tb, float* C, const fl
     if (kahan) {
       auto kfn = gemm_tcgen05_kernel<KIND, decltype(FMT), true>;
       if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES) != cudaSuccess) rc = -3;
-      else kfn<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(ta, tb, out, kbias, M, N, K, elem_bytes, kblocks_per_slice, idesc, FMT, kblocks_per_split, tiles_m, tiles_n, splits);
+      else kfn<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(ta, tb, out, kbias, M, N, K, elem_bytes, kblocks_per_slice, idesc, FMT, kblocks_per_split, tiles_m, tiles_n, splits, conv);
     } else {
       auto kfn = gemm_tcgen05_kernel<KIND, decltype(FMT), false>;
       if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES) != cudaSuccess) rc = -3;
-      else kfn<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(ta, tb, out, kbias, M, N, K, elem_bytes, kblocks_per_slice, idesc, FMT, kblocks_per_split, tiles_m, tiles_n, splits);
+      else kfn<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(ta, tb, out, kbias, M, N, K, elem_bytes, kblocks_per_slice, idesc, FMT, kblocks_per_split, tiles_m, tiles_n, splits, conv);
     }
     if (rc == 0 && splits > 1) {
       const long long MN = (long long)M * N;
@@ -310,7 +374,7 @@ int launch_kind(const CUtensorMap& ta, const CUtensorMap& tb, float* C, const fl
 // operand_mode: 0 bf16 (kind::f16), 1 fp32 read as tf32 (kind::tf32), 2 e4m3, 3 e5m2 (kind::f8f6f4)
 int gemm_tc_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, int e, int m, bool kahan, int k_slice,
                  int operand_mode, const float* bias, int variant, cudaStream_t st, long long lda, long long ldb, int splits,
-                 float* workspace) {
+                 float* workspace, const ConvGeom* conv) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (lda <= 0) lda = K;
   if (ldb <= 0) ldb = K;
@@ -319,7 +383,7 @@ int gemm_tc_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, i
   // CTA-pair kernel when it covers the format and its 256x256 tiles still fill the machine
   // (Kahan's four casts per element make the kernel requant-bound either way; measured slightly faster on 128x128 tiles)
   if (splits == 1 && (variant == 2 || (variant == 0 && !kahan && 2 * ((M + 255) / 256) * ((N + 255) / 256) >= device_sm_count(-1)))) {
-    const int rc = gemm_tc2_cuda(A, Bt, C, M, N, K, e, m, kahan, k_slice, operand_mode, bias, st, lda, ldb);
+    const int rc = gemm_tc2_cuda(A, Bt, C, M, N, K, e, m, kahan, k_slice, operand_mode, bias, st, lda, ldb, conv);
     if (rc == 0 || variant == 2) return rc;
   }
   int elem_bytes, kind;
@@ -331,6 +395,10 @@ int gemm_tc_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, i
     case 2: elem_bytes = 1; kind = 2; fmt_code = 0; dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; break;
     case 3: elem_bytes = 1; kind = 2; fmt_code = 1; dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; break;
     default: return -1;
+  }
+  if (conv) {
+    if (!conv_geom_ok(*conv, elem_bytes, M, K)) return -7;
+    lda = K;
   }
   if ((lda * elem_bytes) % 16 != 0 || (ldb * elem_bytes) % 16 != 0) return -2;       // TMA global stride must be a multiple of 16 B
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt)) & 15u) return -2;
@@ -345,13 +413,15 @@ int gemm_tc_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, i
   const int kblocks_per_split = slices_per_split * kblocks_per_slice;
   splits = (total_kblocks + kblocks_per_split - 1) / kblocks_per_split;
   CUtensorMap ta, tb;
-  if (!make_tmap(&ta, A, M, K, lda, elem_bytes, dt) || !make_tmap(&tb, Bt, N, K, ldb, elem_bytes, dt)) return -4;
+  if (!(conv ? make_tmap_im2col(&ta, A, *conv, elem_bytes, dt, tc::BLOCK_M) : make_tmap(&ta, A, M, K, lda, elem_bytes, dt)) ||
+      !make_tmap(&tb, Bt, N, K, ldb, elem_bytes, dt)) return -4;
+  const tc::ConvA cgeom = conv_device_geom(conv, elem_bytes);
   // instruction descriptor: D fp32 | A/B format | K-major both | N >> 3 | M >> 4
   const uint32_t idesc = (1u << 4) | (fmt_code << 7) | (fmt_code << 10) | ((uint32_t)(tc::BLOCK_N >> 3) << 17) |
                          ((uint32_t)(tc::BLOCK_M >> 4) << 24);
-  if (kind == 0) return launch_kind<0>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st, splits, kblocks_per_split, workspace);
-  if (kind == 1) return launch_kind<1>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st, splits, kblocks_per_split, workspace);
-  return launch_kind<2>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st, splits, kblocks_per_split, workspace);
+  if (kind == 0) return launch_kind<0>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st, splits, kblocks_per_split, workspace, cgeom);
+  if (kind == 1) return launch_kind<1>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st, splits, kblocks_per_split, workspace, cgeom);
+  return launch_kind<2>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st, splits, kblocks_per_split, workspace, cgeom);
 }
 
 }  // namespace cpd

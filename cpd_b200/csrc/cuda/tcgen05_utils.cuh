@@ -41,6 +41,24 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       :: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// im2col-mode TMA (implicit-GEMM convolution): loads pixelsPerColumn consecutive OUTPUT positions of an NHWC tensor,
+// starting at base pixel (w, h, n) = (q * stride - pad, p * stride - pad, image), for the filter tap (off_w, off_h) and
+// the channel block starting at c.  The hardware walks q -> p -> n inside the descriptor's bounding box with the
+// traversal stride and zero-fills the padding halo: the [pixels][channels] box lands in shared memory exactly like a
+// tiled 2-D box of an explicit im2col matrix (128-byte rows, SWIZZLE_128B), which is never materialised.
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      :: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+// Geometry of an implicit-GEMM A operand (cblocks == 0: A is a plain K-major matrix).  K-block kb of the GEMM is filter
+// tap kb / cblocks (row-major over KH x KW) and channel block kb % cblocks.
+struct ConvA {
+  int cblocks;        // channel blocks of one tap = C / (128 B / element size); 0 = not a convolution
+  int OHW, OW;        // output positions per image / per row
+  int stride, pad, dil, KW;
+};
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" :: "l"(tmap) : "memory");
 }
@@ -131,6 +149,13 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       :: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_2cta(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c, int w, int h, int n,
+                                                        uint16_t off_w, uint16_t off_h) {
+  const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      :: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(leader_bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smem_dst)), "r"(cols) : "memory");

@@ -183,6 +183,43 @@ def gemm_tc(a: torch.Tensor, bt: torch.Tensor, exp: int, man: int, kahan: bool =
     return out
 
 
+def conv_implicit_ok(C: int, kh: int, kw: int, stride: int, pad: int, dil: int, operand_mode: int) -> bool:
+    """Does the implicit-GEMM (im2col-mode TMA) path cover this convolution?  Whole 128-byte channel blocks per tap and
+    the descriptor's corner / offset ranges; everything else goes through the explicit staging kernel."""
+    cpb = 128 // _OPERAND_TORCH[operand_mode].itemsize
+    return (C > 0 and C % cpb == 0 and 1 <= stride <= 8 and dil >= 1 and 0 <= pad <= 127 and (kh - 1) * dil <= 255 and
+            (kw - 1) * dil <= 255 and pad - (kh - 1) * dil >= -128 and pad - (kw - 1) * dil >= -128)
+
+
+def gemm_conv(x_nhwc: torch.Tensor, bt: torch.Tensor, kh: int, kw: int, out_hw, stride: int, pad: int, dil: int, exp: int, man: int,
+              kahan: bool = False, k_slice: int = 128, operand_mode: int = OPERAND_BF16, bias: Optional[torch.Tensor] = None,
+              variant: int = GEMM_AUTO) -> torch.Tensor:
+    """Implicit-GEMM convolution on tcgen05: y[(b,oh,ow), o] = sum_(kh,kw,c) x[b, oh*s-p+kh*d, ow*s-p+kw*d, c] * bt[o, (kh,kw,c)].
+    ``x_nhwc`` is the dense [B, H, W, C] activation tensor ALREADY in the operand dtype; the im2col matrix is never
+    written: the kernel's TMA producer reads the taps straight from it (im2col-mode tensor map, zero-filled halo).
+    ``bt`` [O, >= KH*KW*C] K-major filter matrix.  Accumulator re-quantised to (exp, man) every ``k_slice``."""
+    _check_fmt(exp, man)
+    want = _OPERAND_TORCH[operand_mode]
+    if not (x_nhwc.is_cuda and x_nhwc.dim() == 4 and x_nhwc.is_contiguous() and x_nhwc.dtype == want):
+        raise ValueError(f"gemm_conv: dense [B, H, W, C] {want} CUDA tensor expected")
+    B, H, W, C = x_nhwc.shape
+    OH, OW = int(out_hw[0]), int(out_hw[1])
+    K = kh * kw * C
+    if not (bt.is_cuda and bt.dim() == 2 and bt.stride(1) == 1 and bt.dtype == want and bt.shape[1] >= K):
+        raise ValueError("gemm_conv: K-major filter matrix [O, KH*KW*C] in the operand dtype expected")
+    if not conv_implicit_ok(C, kh, kw, stride, pad, dil, operand_mode):
+        raise ValueError("gemm_conv: convolution not covered by the implicit-GEMM path (see conv_implicit_ok)")
+    O = bt.shape[0]
+    out = torch.empty(B * OH * OW, O, dtype=torch.float32, device=x_nhwc.device)
+    with torch.cuda.device(x_nhwc.device):
+        rc = _C.gemm_conv_cuda(x_nhwc.data_ptr(), bt.data_ptr(), out.data_ptr(), O, [B, H, W, C, kh, kw, OH, OW, stride, pad, dil],
+                               int(exp), int(man), bool(kahan), int(k_slice), int(operand_mode), _ptr(bias), int(variant),
+                               _stream(x_nhwc), int(bt.stride(0) if O > 1 else bt.shape[1]))
+    if rc != 0:
+        raise RuntimeError(f"gemm_conv: kernel rejected the problem (code {rc})")
+    return out
+
+
 # ---- operand staging: gather / im2col + cast in one kernel (cuda/operand_stage_sm100.cu) -----------------------------
 def _staged_empty(R: int, K: int, operand_mode: int, device) -> torch.Tensor:
     Kp = (K + 15) // 16 * 16           # 16-byte rows for every operand type (TMA global stride)

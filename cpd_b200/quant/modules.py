@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -69,6 +70,17 @@ class Quant_LinearFunction(Function):
         return grad_input, grad_weight, grad_bias, None, None, None
 
 
+_IMPLICIT = os.environ.get("CPD_B200_CONV_IMPLICIT", "0") != "0"       # implicit-GEMM (im2col-mode TMA) convolutions where covered
+
+
+def _nhwc_rows(x):
+    """[B*H*W, C] view of a channels_last [B, C, H, W] tensor (None when x is laid out otherwise)."""
+    B, C, H, W = x.shape
+    if x.stride() == (H * W * C, 1, W * C, C) or (C == 1 and x.is_contiguous()):
+        return x.as_strided((B * H * W, C), (C, 1), x.storage_offset())
+    return None
+
+
 class Quant_ConvTileFunction(Function):
     """2-D convolution whose three GEMMs run on the tensor cores with the accumulator at (exp, man), WITHOUT the
     reference's glue (quant_module.py:115-139: F.unfold's fp32 column matrix, transposed copies, separate bias add and
@@ -92,10 +104,15 @@ class Quant_ConvTileFunction(Function):
         OW = (W + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
         om = operand_mode_for(exp, man, operands)
         ws = weight.stride()
-        a, bt = native.stage(native.spec_im2col(x, KH, KW, (OH, OW), stride, padding, dilation, om),
-                             native.spec_gather(weight, O, (KH, KW, C), (ws[2], ws[3], ws[1]), ws[0], om))
-        K = KH * KW * C
-        y = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, bias, k=K)                      # [B*OH*OW, O] == NHWC
+        wspec = native.spec_gather(weight, O, (KH, KW, C), (ws[2], ws[3], ws[1]), ws[0], om)
+        x2 = _nhwc_rows(x)
+        if x2 is not None and _IMPLICIT and native.conv_implicit_ok(C, KH, KW, stride, padding, dilation, om):
+            # implicit GEMM: the staging launch only CASTS x (2 bytes written per element instead of KH*KW of them)
+            a, bt = native.stage(native.spec_matrix(x2, om), wspec)
+            y = native.gemm_conv(a.view(B, H, W, C), bt, KH, KW, (OH, OW), stride, padding, dilation, exp, man, kahan, k_slice, om, bias)
+        else:
+            a, bt = native.stage(native.spec_im2col(x, KH, KW, (OH, OW), stride, padding, dilation, om), wspec)
+            y = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, bias, k=KH * KW * C)        # [B*OH*OW, O] == NHWC
         ctx.save_for_backward(x, weight)
         ctx.cfg = (exp, man, stride, padding, dilation, k_slice, om, kahan, bias is not None, (OH, OW))
         return y.view(B, OH, OW, O).permute(0, 3, 1, 2)
@@ -111,9 +128,15 @@ class Quant_ConvTileFunction(Function):
         if ctx.needs_input_grad[0]:
             pad_t = dilation * (KH - 1) - padding
             base = (KH - 1) * ws[2] + (KW - 1) * ws[3]
-            a, bt = native.stage(native.spec_im2col(dy, KH, KW, (H, W), 1, pad_t, dilation, om, in_dil=stride),        # [(b,h,w), (kh,kw,o)]
-                                 native.spec_gather(weight, C, (KH, KW, O), (-ws[2], -ws[3], ws[0]), ws[1], om, base=base))   # flipped filter
-            g = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, None, k=KH * KW * O)             # [(b,h,w), c] == NHWC
+            wspec = native.spec_gather(weight, C, (KH, KW, O), (-ws[2], -ws[3], ws[0]), ws[1], om, base=base)     # flipped filter
+            dy2 = _nhwc_rows(dy)
+            if (dy2 is not None and _IMPLICIT and stride == 1 and pad_t >= 0 and
+                    native.conv_implicit_ok(O, KH, KW, 1, pad_t, dilation, om)):
+                a, bt = native.stage(native.spec_matrix(dy2, om), wspec)          # stride-1 data gradient = a convolution of dy
+                g = native.gemm_conv(a.view(B, OH, OW, O), bt, KH, KW, (H, W), 1, pad_t, dilation, exp, man, kahan, k_slice, om)
+            else:
+                a, bt = native.stage(native.spec_im2col(dy, KH, KW, (H, W), 1, pad_t, dilation, om, in_dil=stride), wspec)   # [(b,h,w), (kh,kw,o)]
+                g = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, None, k=KH * KW * O)             # [(b,h,w), c] == NHWC
             dx = g.view(B, H, W, C).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
             ds = dy.stride()
