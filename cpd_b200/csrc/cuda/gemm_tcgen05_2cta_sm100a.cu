@@ -86,7 +86,7 @@ template <int KIND, class ACC, bool KAHAN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc2::NUM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          float* __restrict__ C, const float* __restrict__ bias, int M, int N, int K, int elem_bytes,
-                         int kblocks_per_slice, uint32_t idesc, int tiles_n, int num_tiles, tc::ConvA conv) {
+                         int kblocks_per_slice, uint32_t idesc, int tiles_m, int tiles_n, int num_tiles, tc::ConvA conv) {
   using namespace tc2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -101,7 +101,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   // store overlaps tile i+1's first MMAs (the TMEM stage is handed back as soon as it is in registers).
   const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
 #define CPD_TILE2_COORDS(t)                                                                          \
-  const int tile_m = (t) / tiles_n, tile_n = (t) % tiles_n;                                          \
+  const int band_ = (t) / (tc::RASTER_GROUP * tiles_n), bm0_ = band_ * tc::RASTER_GROUP;             \
+  const int bsz_ = min(tc::RASTER_GROUP, tiles_m - bm0_), bi_ = (t) - band_ * (tc::RASTER_GROUP * tiles_n); \
+  const int tile_m = bm0_ + bi_ % bsz_, tile_n = bi_ / bsz_;    /* banded raster, see the 1-CTA kernel */ \
   const int m0 = tile_m * PAIR_M + (int)cta_rank * CTA_M;          /* this CTA's rows of A / C */    \
   const int n0 = tile_n * BLOCK_N;                                                                   \
   const int nb0 = n0 + (int)cta_rank * CTA_BROWS;                  /* this CTA's rows of Bt */       \
@@ -329,11 +331,11 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, float* C, const float*
   if (kahan) {
     auto kfn = gemm_tcgen05_2cta_kernel<KIND, ACC, true>;
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES) != cudaSuccess) return -3;
-    kfn<<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, tiles_n, num_tiles, conv);
+    kfn<<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, tiles_m, tiles_n, num_tiles, conv);
   } else {
     auto kfn = gemm_tcgen05_2cta_kernel<KIND, ACC, false>;
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES) != cudaSuccess) return -3;
-    kfn<<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, tiles_n, num_tiles, conv);
+    kfn<<<grid, tc2::NUM_THREADS, tc2::SMEM_BYTES, st>>>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, tiles_m, tiles_n, num_tiles, conv);
   }
   return 0;
 }

@@ -100,8 +100,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tmem_base = bars->tmem_base;
 
   // tile -> (split z, n-tile, m-tile) and the split's K-block range
+  // Raster: bands of RASTER_GROUP m-tiles, m fastest inside a band, then n, then the next band - the tiles in flight
+  // at any moment (one per SM) form a ~8 x 18 block of the tile grid and share ~26 operand tiles instead of ~150
+  // (m-fastest over the whole matrix re-read A once per n-tile: the 32768 x 256 x 2304 convolution GEMM lost 12 %).
 #define CPD_TILE_COORDS(t)                                                                          \
-  const int tm_ = (t) % tiles_m, tn_ = ((t) / tiles_m) % tiles_n, tz_ = (t) / (tiles_m * tiles_n);   \
+  const int tz_ = (t) / (tiles_m * tiles_n), tr_ = (t) - tz_ * (tiles_m * tiles_n);                  \
+  const int band_ = tr_ / (RASTER_GROUP * tiles_n), bm0_ = band_ * RASTER_GROUP;                     \
+  const int bsz_ = min(RASTER_GROUP, tiles_m - bm0_), bi_ = tr_ - band_ * (RASTER_GROUP * tiles_n);  \
+  const int tm_ = bm0_ + bi_ % bsz_, tn_ = bi_ / bsz_;                                              \
   const int m0 = tm_ * BLOCK_M, n0 = tn_ * BLOCK_N;                                                 \
   const int kb0 = tz_ * kblocks_per_split;                                                          \
   const int num_kblocks = max(0, min(total_kblocks - kb0, kblocks_per_split));                      \

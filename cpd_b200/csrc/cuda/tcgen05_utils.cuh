@@ -52,6 +52,8 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtenso
       "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
       :: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
 }
+constexpr int RASTER_GROUP = 8;      // m-tiles per raster band of the persistent GEMMs' tile order
+
 // Geometry of an implicit-GEMM A operand (cblocks == 0: A is a plain K-major matrix).  K-block kb of the GEMM is filter
 // tap kb / cblocks (row-major over KH x KW) and channel block kb % cblocks.
 struct ConvA {

@@ -5,6 +5,10 @@ set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 OUT=gpurun_out/r2t9; mkdir -p $OUT
 timeout 300 python -m pytest tests/test_gpu_implicit_conv.py -q -x > $OUT/pytest_implicit.log 2>&1; echo "implicit tests rc=$?"; tail -15 $OUT/pytest_implicit.log
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_staging.py -q -x > $OUT/pytest_gemm.log 2>&1; echo "gemm+staging tests rc=$?"; tail -3 $OUT/pytest_gemm.log
+timeout 600 python tools/bench_gemm.py --quick > $OUT/bench_gemm.json 2> $OUT/bench_gemm.err; echo "rc=$?"; python -c "
+import json; d=json.load(open('$OUT/bench_gemm.json'))
+for r in d['gemm_tc']: print({k: r[k] for k in r if k in ('M','N','K','acc','k_slice','variant','ms','TFLOPs','cublas_ms','cublas_TFLOPs')})"
 for imp in 0 1; do
   CPD_B200_CONV_IMPLICIT=$imp timeout 400 python bench.py --model resnet18_quant --steps 20 --warmup 3 > $OUT/bench_quant_imp$imp.json 2>> $OUT/bench.err; python -c "
 import json; d=json.loads(open('$OUT/bench_quant_imp$imp.json').read().strip().splitlines()[-1]); print('quant implicit=$imp', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'launches', d.get('gpu_launches'))"
