@@ -155,6 +155,9 @@ void mx_quantize_cuda(const float* in, long long ld_in, uint8_t* codes, uint8_t*
 // block-scaled GEMM (tcgen05.mma.kind::mxf8f6f4.block_scale) with per-K-slice accumulator requant
 int gemm_tc_mx_cuda(const uint8_t* codes_a, const uint8_t* sf_a, const uint8_t* codes_b, const uint8_t* sf_b, float* C, int M, int N,
                     int Kp, int e, int m, bool kahan, int k_slice, bool e5m2, const float* bias, cudaStream_t st);
+// weight gradient of a convolution as an implicit GEMM (MN-major operand tiles; bf16 operands): see gemm_tcgen05_sm100a.cu
+int gemm_wgrad_cuda(const void* dY, const void* X, float* dW, const ConvGeom& g, int O, int e, int m, bool kahan, int k_slice,
+                    cudaStream_t st, int splits = 1, float* workspace = nullptr, int lbo = 0, int sbo = 0);
 int gemm_tc2_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, int e, int m, bool kahan, int k_slice,
                   int operand_mode, const float* bias, cudaStream_t st, long long lda = 0, long long ldb = 0,
                   const ConvGeom* conv = nullptr);

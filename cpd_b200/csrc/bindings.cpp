@@ -112,6 +112,19 @@ PYBIND11_MODULE(_C, m) {
   }, py::arg("X"), py::arg("Bt"), py::arg("C"), py::arg("N"), py::arg("geom"), py::arg("e"), py::arg("m"), py::arg("kahan"),
      py::arg("k_slice"), py::arg("operand_mode"), py::arg("bias"), py::arg("variant"), py::arg("stream"), py::arg("ldb") = 0);
 
+  m.def("gemm_wgrad_cuda", [](uptr dY, uptr X, uptr dW, int O, std::vector<int> geom, int e, int mb, bool kahan, int k_slice,
+                              uptr stream, int splits, uptr workspace, int lbo, int sbo) {
+    check_fmt(e, mb);
+    if (geom.size() != 11) throw std::invalid_argument("gemm_wgrad: geom = (B, H, W, C, KH, KW, OH, OW, stride, pad, dil)");
+    cpd::ConvGeom g{geom[0], geom[1], geom[2], geom[3], geom[4], geom[5], geom[6], geom[7], geom[8], geom[9], geom[10]};
+    int rc = cpd::gemm_wgrad_cuda(P<const void>(dY), P<const void>(X), P<float>(dW), g, O, e, mb, kahan, k_slice, S(stream), splits,
+                                  P<float>(workspace), lbo, sbo);
+    if (splits > 1 && rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);      // + the split-K fold kernel
+    check_launch("gemm_wgrad");
+    return rc;
+  }, py::arg("dY"), py::arg("X"), py::arg("dW"), py::arg("O"), py::arg("geom"), py::arg("e"), py::arg("m"), py::arg("kahan"),
+     py::arg("k_slice"), py::arg("stream"), py::arg("splits") = 1, py::arg("workspace") = (uptr)0, py::arg("lbo") = 0, py::arg("sbo") = 0);
+
   // operand staging: fp32 -> tensor-core operand (gather / im2col + cast), see cuda/operand_stage_sm100.cu.
   // Descriptors are built once (opaque bytes) and one launch stages one or BOTH operands of a GEMM.
   m.def("stage_gather_desc", [](uptr src, int64_t base, int rows_fast, int64_t s_row, int64_t s1, int64_t s2, int64_t s3, int n2, int n3) {

@@ -132,6 +132,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t ph = (it / NUM_STAGES) & 1;
           mbar_wait(&bars->empty[s], ph ^ 1);
           mbar_expect_tx(&bars->full[s], A_STAGE_BYTES + B_STAGE_BYTES);
+          if (conv.wgrad) {
+            const int pix0 = (kb0 + kb) * 64;                        // K-block = 64 output positions
+            const int pn = pix0 / conv.OHW, rem = pix0 - pn * conv.OHW, pp = rem / conv.OW;
+            const int ph_ = pp * conv.stride - conv.pad, pw_ = (rem - pp * conv.OW) * conv.stride - conv.pad;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              tma_load_2d(smem_a + s * A_STAGE_BYTES + j * (A_STAGE_BYTES / 2), &tmap_a, &bars->full[s], m0 + 64 * j, pix0);
+              int tap = (n0 + 64 * j) / conv.C;
+              const int c = (n0 + 64 * j) - tap * conv.C;
+              tap = min(tap, conv.taps - 1);                         // columns past N are computed on a valid tap and never stored
+              const int r = tap / conv.KW, sx = tap - r * conv.KW;
+              tma_load_im2col_4d(smem_b + s * B_STAGE_BYTES + j * (B_STAGE_BYTES / 2), &tmap_b, &bars->full[s], c, pw_, ph_, pn,
+                                 (uint16_t)(sx * conv.dil), (uint16_t)(r * conv.dil));
+            }
+            continue;
+          }
           if (conv.cblocks) {
             const int tap = (kb0 + kb) / conv.cblocks, cb = (kb0 + kb) - tap * conv.cblocks;
             const int r = tap / conv.KW, sx = tap - r * conv.KW;
@@ -164,12 +180,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t ph = (it / NUM_STAGES) & 1;
             mbar_wait(&bars->full[s], ph);
             tc_fence_after();
+            if (conv.wgrad) {                                          // MN-major tiles: 16 pixels (K) = 2048 B per instruction
+              const uint64_t adesc = make_smem_desc_mn(smem_u32(smem_a + s * A_STAGE_BYTES), conv.lbo, conv.sbo);
+              const uint64_t bdesc = make_smem_desc_mn(smem_u32(smem_b + s * B_STAGE_BYTES), conv.lbo, conv.sbo);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma<KIND>(d_addr, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, first ? 0u : 1u);
+                first = false;
+              }
+            } else {
             const uint64_t adesc = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
             const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
 #pragma unroll
             for (int k = 0; k < STAGE_ROW_BYTES / 32; ++k) {          // 32 bytes of K per instruction
               umma<KIND>(d_addr, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
               first = false;
+            }
             }
             umma_commit(&bars->empty[s]);                              // smem stage reusable once these MMAs retire
           }
@@ -266,12 +292,13 @@ PFN_encodeTiled get_encode() {
 }
 
 // 2-D row-major [rows, K] operand, box = {128 B of K, 128 rows}, 128B swizzle, zero fill out of bounds
-bool make_tmap(CUtensorMap* tm, const void* base, int rows, int K, long long ld, int elem_bytes, CUtensorMapDataType dt) {
+bool make_tmap(CUtensorMap* tm, const void* base, int rows, int K, long long ld, int elem_bytes, CUtensorMapDataType dt,
+               int box_rows = tc::BLOCK_M) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};          // the TRUE K: the tail of the last box is zero-filled
   cuuint64_t gstride[1] = {(cuuint64_t)ld * elem_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)(tc::STAGE_ROW_BYTES / elem_bytes), (cuuint32_t)tc::BLOCK_M};
+  cuuint32_t box[2] = {(cuuint32_t)(tc::STAGE_ROW_BYTES / elem_bytes), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return enc(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -316,7 +343,7 @@ bool conv_geom_ok(const ConvGeom& g, int elem_bytes, int M, int K) {
 }
 
 tc::ConvA conv_device_geom(const ConvGeom* g, int elem_bytes) {
-  tc::ConvA c = {0, 1, 1, 1, 0, 1, 1};
+  tc::ConvA c = {0, 1, 1, 1, 0, 1, 1, 0, 1, 1, 8192, 1024};
   if (g) {
     c.cblocks = g->C / (tc::STAGE_ROW_BYTES / elem_bytes);
     c.OHW = g->OH * g->OW; c.OW = g->OW; c.stride = g->stride; c.pad = g->pad; c.dil = g->dil; c.KW = g->KW;
@@ -428,6 +455,44 @@ int gemm_tc_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, i
   if (kind == 0) return launch_kind<0>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st, splits, kblocks_per_split, workspace, cgeom);
   if (kind == 1) return launch_kind<1>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st, splits, kblocks_per_split, workspace, cgeom);
   return launch_kind<2>(ta, tb, C, bias, M, N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st, splits, kblocks_per_split, workspace, cgeom);
+}
+
+
+// Weight gradient of a convolution as an implicit GEMM: dW[O, KH*KW*C] = dy[pixels, O]^T . im2col(x)[pixels, KH*KW*C],
+// reduction over pixels = B*OH*OW (split-K + ordered fold as in gemm_tc_cuda).  dY: [pixels, O] and X: [B, H, W, C], both
+// dense bf16; neither a transposed dy nor a transposed im2col matrix is ever written (MN-major operand tiles).
+int gemm_wgrad_cuda(const void* dY, const void* X, float* dW, const ConvGeom& g, int O, int e, int m, bool kahan, int k_slice,
+                    cudaStream_t st, int splits, float* workspace, int lbo, int sbo) {
+  const int elem_bytes = 2;
+  const long long pixels = (long long)g.B * g.OH * g.OW, N = (long long)g.KH * g.KW * g.C;
+  if (O <= 0 || pixels <= 0 || pixels > INT32_MAX || N > INT32_MAX) return -1;
+  if (!conv_geom_ok(g, elem_bytes, (int)pixels, (int)N)) return -7;
+  if ((O * elem_bytes) % 16 != 0) return -2;
+  if ((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(X)) & 15u) return -2;
+  if (splits < 1) splits = 1;
+  if (splits > 1 && !workspace) return -6;
+  const int M = O, K = (int)pixels;
+  const int total_kblocks = (K + 63) / 64;
+  int kblocks_per_slice = k_slice <= 0 ? total_kblocks : (k_slice + 63) / 64;
+  if (kblocks_per_slice < 1) kblocks_per_slice = 1;
+  const int slices = (total_kblocks + kblocks_per_slice - 1) / kblocks_per_slice;
+  if (splits > slices) splits = slices;
+  const int slices_per_split = (slices + splits - 1) / splits;
+  const int kblocks_per_split = slices_per_split * kblocks_per_slice;
+  splits = (total_kblocks + kblocks_per_split - 1) / kblocks_per_split;
+  CUtensorMap ta, tb;
+  // dy as a 2-D tensor [pixels rows, O contiguous]: box = {64 o (128 B), 64 pixels}
+  if (!make_tmap(&ta, dY, K, O, O, elem_bytes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 64) ||
+      !make_tmap_im2col(&tb, X, g, elem_bytes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 64)) return -4;
+  tc::ConvA c = conv_device_geom(&g, elem_bytes);
+  c.wgrad = 1; c.C = g.C; c.taps = g.KH * g.KW;
+  c.lbo = lbo > 0 ? lbo : tc::A_STAGE_BYTES / 2;
+  c.sbo = sbo > 0 ? sbo : 1024;
+  // bf16 | A and B MN-major (bits 15, 16) | N >> 3 | M >> 4
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(tc::BLOCK_N >> 3) << 17) |
+                         ((uint32_t)(tc::BLOCK_M >> 4) << 24);
+  return launch_kind<0>(ta, tb, dW, nullptr, M, (int)N, K, elem_bytes, kblocks_per_slice, idesc, e, m, kahan, st, splits, kblocks_per_split,
+                        workspace, c);
 }
 
 }  // namespace cpd

@@ -56,11 +56,28 @@ constexpr int RASTER_GROUP = 8;      // m-tiles per raster band of the persisten
 
 // Geometry of an implicit-GEMM A operand (cblocks == 0: A is a plain K-major matrix).  K-block kb of the GEMM is filter
 // tap kb / cblocks (row-major over KH x KW) and channel block kb % cblocks.
+//
+// wgrad != 0: WEIGHT-GRADIENT mode - dW[o, (kh,kw,c)] = sum_pixels dy[pixel, o] * im2col(x)[pixel, (kh,kw,c)].  Both
+// operands have the reduction index (pixel) as their SLOW memory dimension, so they are fed MN-major: a K-block is 64
+// pixels; A = two tiled boxes {64 o, 64 pixels} of dy [pixels, O]; B = two im2col boxes {64 channels, 64 pixels} of x
+// (one per 64 columns of the (tap, c) tile).  Shared-memory rows are then pixels (K) of 128 bytes of M / N, and the
+// MMA descriptors say MN-major (lbo = distance between the two 64-wide chunks, sbo = between 8-pixel groups).
 struct ConvA {
   int cblocks;        // channel blocks of one tap = C / (128 B / element size); 0 = not a convolution
   int OHW, OW;        // output positions per image / per row
   int stride, pad, dil, KW;
+  int wgrad, C, taps; // weight-gradient mode, channels, KH * KW
+  int lbo, sbo;       // MN-major descriptor strides in bytes (wgrad mode)
 };
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, int lbo, int sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" :: "l"(tmap) : "memory");
 }

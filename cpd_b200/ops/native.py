@@ -220,6 +220,35 @@ def gemm_conv(x_nhwc: torch.Tensor, bt: torch.Tensor, kh: int, kw: int, out_hw, 
     return out
 
 
+def gemm_wgrad(dy_rows: torch.Tensor, x_nhwc: torch.Tensor, kh: int, kw: int, out_hw, stride: int, pad: int, dil: int, exp: int,
+               man: int, kahan: bool = False, k_slice: int = 128, splits: int = 1, _lbo: int = 0, _sbo: int = 0) -> torch.Tensor:
+    """Weight gradient of a convolution as an implicit GEMM: dW[o, (kh,kw,c)] = sum_pixels dy[pixel, o] * x-tap[pixel, (kh,kw,c)].
+    ``dy_rows`` [B*OH*OW, O] and ``x_nhwc`` [B, H, W, C] dense bf16.  Both operands are read MN-major straight from those
+    tensors (tiled TMA for dy, im2col-mode TMA for x): no transposed copy of dy, no (transposed) im2col matrix.  The long
+    reduction over pixels runs split-K with the ordered quantised fold of ``gemm_tc``."""
+    _check_fmt(exp, man)
+    if not (x_nhwc.is_cuda and x_nhwc.dim() == 4 and x_nhwc.is_contiguous() and x_nhwc.dtype == torch.bfloat16):
+        raise ValueError("gemm_wgrad: dense [B, H, W, C] bf16 CUDA tensor expected")
+    B, H, W, C = x_nhwc.shape
+    OH, OW = int(out_hw[0]), int(out_hw[1])
+    if not (dy_rows.is_cuda and dy_rows.dim() == 2 and dy_rows.is_contiguous() and dy_rows.dtype == torch.bfloat16 and
+            dy_rows.shape[0] == B * OH * OW):
+        raise ValueError("gemm_wgrad: dense [B*OH*OW, O] bf16 gradient expected")
+    O = dy_rows.shape[1]
+    if O % 8 or not conv_implicit_ok(C, kh, kw, stride, pad, dil, OPERAND_BF16):
+        raise ValueError("gemm_wgrad: convolution not covered by the implicit-GEMM path")
+    N = kh * kw * C
+    out = torch.empty(O, N, dtype=torch.float32, device=x_nhwc.device)
+    splits = max(1, int(splits))
+    ws = torch.empty(splits, O, N, dtype=torch.float32, device=x_nhwc.device) if splits > 1 else None
+    with torch.cuda.device(x_nhwc.device):
+        rc = _C.gemm_wgrad_cuda(dy_rows.data_ptr(), x_nhwc.data_ptr(), out.data_ptr(), O, [B, H, W, C, kh, kw, OH, OW, stride, pad, dil],
+                                int(exp), int(man), bool(kahan), int(k_slice), _stream(x_nhwc), splits, _ptr(ws), int(_lbo), int(_sbo))
+    if rc != 0:
+        raise RuntimeError(f"gemm_wgrad: kernel rejected the problem (code {rc})")
+    return out
+
+
 # ---- operand staging: gather / im2col + cast in one kernel (cuda/operand_stage_sm100.cu) -----------------------------
 def _staged_empty(R: int, K: int, operand_mode: int, device) -> torch.Tensor:
     Kp = (K + 15) // 16 * 16           # 16-byte rows for every operand type (TMA global stride)

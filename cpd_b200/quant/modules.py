@@ -106,45 +106,58 @@ class Quant_ConvTileFunction(Function):
         ws = weight.stride()
         wspec = native.spec_gather(weight, O, (KH, KW, C), (ws[2], ws[3], ws[1]), ws[0], om)
         x2 = _nhwc_rows(x)
-        if x2 is not None and _IMPLICIT and native.conv_implicit_ok(C, KH, KW, stride, padding, dilation, om):
+        implicit = x2 is not None and _IMPLICIT and native.conv_implicit_ok(C, KH, KW, stride, padding, dilation, om)
+        if implicit:
             # implicit GEMM: the staging launch only CASTS x (2 bytes written per element instead of KH*KW of them)
             a, bt = native.stage(native.spec_matrix(x2, om), wspec)
             y = native.gemm_conv(a.view(B, H, W, C), bt, KH, KW, (OH, OW), stride, padding, dilation, exp, man, kahan, k_slice, om, bias)
         else:
             a, bt = native.stage(native.spec_im2col(x, KH, KW, (OH, OW), stride, padding, dilation, om), wspec)
             y = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, bias, k=KH * KW * C)        # [B*OH*OW, O] == NHWC
-        ctx.save_for_backward(x, weight)
-        ctx.cfg = (exp, man, stride, padding, dilation, k_slice, om, kahan, bias is not None, (OH, OW))
+        # the weight gradient reads the SAME bf16 copy of x (implicit GEMM again): keep that instead of the fp32 input
+        keep_cast = implicit and om == native.OPERAND_BF16 and O % 8 == 0
+        ctx.save_for_backward(a.view(B, H, W, C) if keep_cast else x, weight)
+        ctx.cfg = (exp, man, stride, padding, dilation, k_slice, om, kahan, bias is not None, (OH, OW), keep_cast, (B, C, H, W))
         return y.view(B, OH, OW, O).permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
-        exp, man, stride, padding, dilation, k_slice, om, kahan, has_bias, (OH, OW) = ctx.cfg
-        B, C, H, W = x.shape
+        exp, man, stride, padding, dilation, k_slice, om, kahan, has_bias, (OH, OW), x_is_cast, (B, C, H, W) = ctx.cfg
         O, _, KH, KW = weight.shape
         dx = dw = db = None
         ws = weight.stride()
+        dy2 = _nhwc_rows(dy)
+        if x_is_cast and dy2 is None:                       # the implicit weight gradient wants dy as [pixels, O] rows
+            dy = dy.contiguous(memory_format=torch.channels_last)
+            dy2 = _nhwc_rows(dy)
+        dy_cast = None                                      # dy in the operand dtype, [B*OH*OW, O]
         if ctx.needs_input_grad[0]:
             pad_t = dilation * (KH - 1) - padding
             base = (KH - 1) * ws[2] + (KW - 1) * ws[3]
             wspec = native.spec_gather(weight, C, (KH, KW, O), (-ws[2], -ws[3], ws[0]), ws[1], om, base=base)     # flipped filter
-            dy2 = _nhwc_rows(dy)
             if (dy2 is not None and _IMPLICIT and stride == 1 and pad_t >= 0 and
                     native.conv_implicit_ok(O, KH, KW, 1, pad_t, dilation, om)):
-                a, bt = native.stage(native.spec_matrix(dy2, om), wspec)          # stride-1 data gradient = a convolution of dy
-                g = native.gemm_conv(a.view(B, OH, OW, O), bt, KH, KW, (H, W), 1, pad_t, dilation, exp, man, kahan, k_slice, om)
+                dy_cast, bt = native.stage(native.spec_matrix(dy2, om), wspec)    # stride-1 data gradient = a convolution of dy
+                g = native.gemm_conv(dy_cast.view(B, OH, OW, O), bt, KH, KW, (H, W), 1, pad_t, dilation, exp, man, kahan, k_slice, om)
             else:
                 a, bt = native.stage(native.spec_im2col(dy, KH, KW, (H, W), 1, pad_t, dilation, om, in_dil=stride), wspec)   # [(b,h,w), (kh,kw,o)]
                 g = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, None, k=KH * KW * O)             # [(b,h,w), c] == NHWC
             dx = g.view(B, H, W, C).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
-            ds = dy.stride()
             Mred = B * OH * OW
-            a, bt = native.stage(native.spec_gather(dy, O, (B, OH, OW), (ds[0], ds[2], ds[3]), ds[1], om),        # dy^T  [o, (b,oh,ow)]
-                                 native.spec_im2col(x, KH, KW, (OH, OW), stride, padding, dilation, om, taps_are_rows=True))   # [(kh,kw,c), pixels]
             K = KH * KW * C
-            g = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, None, k=Mred, splits=splits_for(O, K, Mred, k_slice))
+            if x_is_cast:
+                # implicit weight gradient: dy [pixels, O] and the bf16 x are read MN-major in place
+                if dy_cast is None:
+                    dy_cast = native.stage(native.spec_matrix(dy2, om))
+                g = native.gemm_wgrad(dy_cast, x, KH, KW, (OH, OW), stride, padding, dilation, exp, man, kahan, k_slice,
+                                      splits=splits_for(O, K, Mred, k_slice))
+            else:
+                ds = dy.stride()
+                a, bt = native.stage(native.spec_gather(dy, O, (B, OH, OW), (ds[0], ds[2], ds[3]), ds[1], om),        # dy^T  [o, (b,oh,ow)]
+                                     native.spec_im2col(x, KH, KW, (OH, OW), stride, padding, dilation, om, taps_are_rows=True))   # [(kh,kw,c), pixels]
+                g = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, None, k=Mred, splits=splits_for(O, K, Mred, k_slice))
             dw = g.view(O, KH, KW, C).permute(0, 3, 1, 2)
         if has_bias and ctx.needs_input_grad[2]:
             if dy.stride(1) == 1 and dy.stride(3) == O and dy.stride(2) == O * OW and dy.stride(0) == O * OW * OH:

@@ -92,3 +92,34 @@ def test_quant_conv_implicit_equals_staged_path(cfg, monkeypatch):
     for a, b in zip(outs[0][:3], outs[1][:3]):
         assert torch.equal(a, b)
     assert outs[1][3] == 2                                   # cast + GEMM
+
+
+def _wgrad_operands(g):
+    B, C, H, W, O, k, stride, pad, dil = g
+    x, w, x_nhwc, wt, (OH, OW) = _operands(g, torch.bfloat16)
+    dy = torch.randn(B, O, OH, OW, device="cuda", generator=torch.Generator("cuda").manual_seed(3)).contiguous(memory_format=torch.channels_last)
+    dy_rows = dy.permute(0, 2, 3, 1).reshape(B * OH * OW, O).contiguous().to(torch.bfloat16)
+    return x, x_nhwc, dy, dy_rows, (OH, OW)
+
+
+@pytest.mark.parametrize("g", [g for g in GEOMS if g[4] % 8 == 0])
+def test_implicit_wgrad_equals_staged_wgrad_bitwise(g):
+    """MN-major implicit weight gradient == the K-major GEMM on the explicitly transposed operands (same K order, same
+    K-slices, same split-K fold) and == autograd's weight gradient in fp32."""
+    B, C, H, W, O, k, stride, pad, dil = g
+    x, x_nhwc, dy, dy_rows, (OH, OW) = _wgrad_operands(g)
+    ds = dy.stride()
+    a, bt = native.stage(native.spec_gather(dy, O, (B, OH, OW), (ds[0], ds[2], ds[3]), ds[1], native.OPERAND_BF16),
+                         native.spec_im2col(x, k, k, (OH, OW), stride, pad, dil, native.OPERAND_BF16, taps_are_rows=True))
+    Mred = B * OH * OW
+    for (e, m, ks, splits) in ((8, 23, 0, 1), (5, 10, 128, 1), (5, 10, 128, 3)):
+        ref = native.gemm_tc(a, bt, e, m, False, ks, native.OPERAND_BF16, None, variant=native.GEMM_1CTA, k=Mred, splits=splits)
+        got = native.gemm_wgrad(dy_rows, x_nhwc, k, k, (OH, OW), stride, pad, dil, e, m, False, ks, splits=splits)
+        assert got.shape == ref.shape == (O, k * k * C)
+        assert torch.equal(got, ref), f"{(got != ref).sum().item()} of {got.numel()} differ, max {(got - ref).abs().max().item()}"
+    wr = torch.zeros(O, C, k, k, device="cuda", requires_grad=True)
+    yr = F.conv2d(x.bfloat16().float(), wr, None, stride=stride, padding=pad, dilation=dil)
+    (dwr,) = torch.autograd.grad(yr, wr, dy.bfloat16().float())
+    got = native.gemm_wgrad(dy_rows, x_nhwc, k, k, (OH, OW), stride, pad, dil, 8, 23, False, 0)
+    got = got.view(O, k, k, C).permute(0, 3, 1, 2)
+    assert (got - dwr).abs().max() <= 2e-4 * dwr.abs().max()
