@@ -99,18 +99,20 @@ PYBIND11_MODULE(_C, m) {
   // implicit-GEMM convolution: X is the NHWC activation tensor in the operand dtype (read through an im2col-mode TMA
   // descriptor), Bt [N, KH*KW*C] the filter matrix in (kh, kw, c) order; geom = (B, H, W, C, KH, KW, OH, OW, stride, pad, dil)
   m.def("gemm_conv_cuda", [](uptr X, uptr Bt, uptr C, int N, std::vector<int> geom, int e, int mb, bool kahan, int k_slice,
-                             int operand_mode, uptr bias, int variant, uptr stream, int64_t ldb) {
+                             int operand_mode, uptr bias, int variant, uptr stream, int64_t ldb, int splits, uptr workspace) {
     check_fmt(e, mb);
     if (geom.size() != 11) throw std::invalid_argument("gemm_conv: geom = (B, H, W, C, KH, KW, OH, OW, stride, pad, dil)");
     cpd::ConvGeom g{geom[0], geom[1], geom[2], geom[3], geom[4], geom[5], geom[6], geom[7], geom[8], geom[9], geom[10]};
     const long long M = (long long)g.B * g.OH * g.OW, K = (long long)g.KH * g.KW * g.C;
     if (M > INT32_MAX || K > INT32_MAX) throw std::invalid_argument("gemm_conv: problem too large");
     int rc = cpd::gemm_tc_cuda(P<const void>(X), P<const void>(Bt), P<float>(C), (int)M, N, (int)K, e, mb, kahan, k_slice, operand_mode,
-                               P<const float>(bias), variant, S(stream), 0, ldb, 1, nullptr, &g);
+                               P<const float>(bias), variant, S(stream), 0, ldb, splits, P<float>(workspace), &g);
+    if (splits > 1 && rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);      // + the split-K fold kernel
     check_launch("gemm_conv");
     return rc;
   }, py::arg("X"), py::arg("Bt"), py::arg("C"), py::arg("N"), py::arg("geom"), py::arg("e"), py::arg("m"), py::arg("kahan"),
-     py::arg("k_slice"), py::arg("operand_mode"), py::arg("bias"), py::arg("variant"), py::arg("stream"), py::arg("ldb") = 0);
+     py::arg("k_slice"), py::arg("operand_mode"), py::arg("bias"), py::arg("variant"), py::arg("stream"), py::arg("ldb") = 0,
+     py::arg("splits") = 1, py::arg("workspace") = (uptr)0);
 
   m.def("gemm_wgrad_cuda", [](uptr dY, uptr X, uptr dW, int O, std::vector<int> geom, int e, int mb, bool kahan, int k_slice,
                               uptr stream, int splits, uptr workspace, int lbo, int sbo) {

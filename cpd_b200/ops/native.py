@@ -193,7 +193,7 @@ def conv_implicit_ok(C: int, kh: int, kw: int, stride: int, pad: int, dil: int, 
 
 def gemm_conv(x_nhwc: torch.Tensor, bt: torch.Tensor, kh: int, kw: int, out_hw, stride: int, pad: int, dil: int, exp: int, man: int,
               kahan: bool = False, k_slice: int = 128, operand_mode: int = OPERAND_BF16, bias: Optional[torch.Tensor] = None,
-              variant: int = GEMM_AUTO) -> torch.Tensor:
+              variant: int = GEMM_AUTO, splits: int = 1) -> torch.Tensor:
     """Implicit-GEMM convolution on tcgen05: y[(b,oh,ow), o] = sum_(kh,kw,c) x[b, oh*s-p+kh*d, ow*s-p+kw*d, c] * bt[o, (kh,kw,c)].
     ``x_nhwc`` is the dense [B, H, W, C] activation tensor ALREADY in the operand dtype; the im2col matrix is never
     written: the kernel's TMA producer reads the taps straight from it (im2col-mode tensor map, zero-filled halo).
@@ -211,10 +211,12 @@ def gemm_conv(x_nhwc: torch.Tensor, bt: torch.Tensor, kh: int, kw: int, out_hw, 
         raise ValueError("gemm_conv: convolution not covered by the implicit-GEMM path (see conv_implicit_ok)")
     O = bt.shape[0]
     out = torch.empty(B * OH * OW, O, dtype=torch.float32, device=x_nhwc.device)
+    splits = max(1, int(splits))
+    ws = torch.empty(splits, B * OH * OW, O, dtype=torch.float32, device=x_nhwc.device) if splits > 1 else None
     with torch.cuda.device(x_nhwc.device):
         rc = _C.gemm_conv_cuda(x_nhwc.data_ptr(), bt.data_ptr(), out.data_ptr(), O, [B, H, W, C, kh, kw, OH, OW, stride, pad, dil],
                                int(exp), int(man), bool(kahan), int(k_slice), int(operand_mode), _ptr(bias), int(variant),
-                               _stream(x_nhwc), int(bt.stride(0) if O > 1 else bt.shape[1]))
+                               _stream(x_nhwc), int(bt.stride(0) if O > 1 else bt.shape[1]), splits, _ptr(ws))
     if rc != 0:
         raise RuntimeError(f"gemm_conv: kernel rejected the problem (code {rc})")
     return out

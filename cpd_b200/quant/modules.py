@@ -70,7 +70,7 @@ class Quant_LinearFunction(Function):
         return grad_input, grad_weight, grad_bias, None, None, None
 
 
-_IMPLICIT = os.environ.get("CPD_B200_CONV_IMPLICIT", "0") != "0"       # implicit-GEMM (im2col-mode TMA) convolutions where covered
+_IMPLICIT = os.environ.get("CPD_B200_CONV_IMPLICIT", "1") != "0"       # implicit-GEMM (im2col-mode TMA) convolutions where covered
 
 
 def _nhwc_rows(x):
@@ -94,7 +94,15 @@ class Quant_ConvTileFunction(Function):
     every operand is produced by ONE fused gather/im2col+cast launch from the fp32 tensor in whatever layout it has
     (NCHW or channels_last), both operands of a GEMM in the same launch; the outputs are channels_last views of the
     GEMM results (no permute copies).  Launches: forward 2 (staging + GEMM, bias fused), backward 2 + 3 (split-K fold)
-    (+1 bias gradient) - against ~25 torch/extension launches per layer in the reference."""
+    (+1 bias gradient) - against ~25 torch/extension launches per layer in the reference.
+
+    IMPLICIT GEMM (default where covered: channels_last input, whole 128-byte channel blocks per tap - every ResNet
+    layer but the 3-channel stem; ``CPD_B200_CONV_IMPLICIT=0`` turns it off): none of the three im2col matrices is
+    written.  The staging launch only casts x / dy; the GEMM kernels read the taps straight from the NHWC tensor with
+    im2col-mode TMA loads (forward, stride-1 data gradient) and, for the weight gradient, read dy and the forward's
+    bf16 x MN-major in place (``native.gemm_conv`` / ``native.gemm_wgrad``).  Same operand values, K order and
+    K-slices as the staged path: bit-identical results (tests/test_gpu_implicit_conv.py).  Launches: forward 2,
+    backward 4.  Under-filled deep layers (few output tiles, long K) run split-K with the ordered quantised fold."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, exp, man, stride, padding, dilation, k_slice, operands, kahan):
@@ -107,13 +115,16 @@ class Quant_ConvTileFunction(Function):
         wspec = native.spec_gather(weight, O, (KH, KW, C), (ws[2], ws[3], ws[1]), ws[0], om)
         x2 = _nhwc_rows(x)
         implicit = x2 is not None and _IMPLICIT and native.conv_implicit_ok(C, KH, KW, stride, padding, dilation, om)
+        # deep layers at small batch leave most SMs idle (32 output tiles, 72 K-blocks each): split-K + ordered fold there too
+        fsplits = splits_for(B * OH * OW, O, KH * KW * C, k_slice)
         if implicit:
             # implicit GEMM: the staging launch only CASTS x (2 bytes written per element instead of KH*KW of them)
             a, bt = native.stage(native.spec_matrix(x2, om), wspec)
-            y = native.gemm_conv(a.view(B, H, W, C), bt, KH, KW, (OH, OW), stride, padding, dilation, exp, man, kahan, k_slice, om, bias)
+            y = native.gemm_conv(a.view(B, H, W, C), bt, KH, KW, (OH, OW), stride, padding, dilation, exp, man, kahan, k_slice, om, bias,
+                                 splits=fsplits)
         else:
             a, bt = native.stage(native.spec_im2col(x, KH, KW, (OH, OW), stride, padding, dilation, om), wspec)
-            y = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, bias, k=KH * KW * C)        # [B*OH*OW, O] == NHWC
+            y = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, bias, k=KH * KW * C, splits=fsplits)        # [B*OH*OW, O] == NHWC
         # the weight gradient reads the SAME bf16 copy of x (implicit GEMM again): keep that instead of the fp32 input
         keep_cast = implicit and om == native.OPERAND_BF16 and O % 8 == 0
         ctx.save_for_backward(a.view(B, H, W, C) if keep_cast else x, weight)
@@ -136,13 +147,15 @@ class Quant_ConvTileFunction(Function):
             pad_t = dilation * (KH - 1) - padding
             base = (KH - 1) * ws[2] + (KW - 1) * ws[3]
             wspec = native.spec_gather(weight, C, (KH, KW, O), (-ws[2], -ws[3], ws[0]), ws[1], om, base=base)     # flipped filter
+            dsplits = splits_for(B * H * W, C, KH * KW * O, k_slice)
             if (dy2 is not None and _IMPLICIT and stride == 1 and pad_t >= 0 and
                     native.conv_implicit_ok(O, KH, KW, 1, pad_t, dilation, om)):
                 dy_cast, bt = native.stage(native.spec_matrix(dy2, om), wspec)    # stride-1 data gradient = a convolution of dy
-                g = native.gemm_conv(dy_cast.view(B, OH, OW, O), bt, KH, KW, (H, W), 1, pad_t, dilation, exp, man, kahan, k_slice, om)
+                g = native.gemm_conv(dy_cast.view(B, OH, OW, O), bt, KH, KW, (H, W), 1, pad_t, dilation, exp, man, kahan, k_slice, om,
+                                     splits=dsplits)
             else:
                 a, bt = native.stage(native.spec_im2col(dy, KH, KW, (H, W), 1, pad_t, dilation, om, in_dil=stride), wspec)   # [(b,h,w), (kh,kw,o)]
-                g = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, None, k=KH * KW * O)             # [(b,h,w), c] == NHWC
+                g = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, None, k=KH * KW * O, splits=dsplits)   # [(b,h,w), c] == NHWC
             dx = g.view(B, H, W, C).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
             Mred = B * OH * OW

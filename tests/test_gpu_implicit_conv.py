@@ -53,6 +53,17 @@ def test_implicit_gemm_equals_explicit_im2col_gemm_bitwise(g, variant):
     assert (got - yr).abs().max() <= 1e-4 * yr.abs().max()
 
 
+def test_implicit_gemm_split_k_equals_explicit_split_k():
+    g = (2, 256, 8, 8, 128, 3, 1, 1, 1)                      # 128 output positions, K = 2304: the under-filled deep-layer shape
+    B, C, H, W, O, k, stride, pad, dil = g
+    x, w, x_nhwc, wt, (OH, OW) = _operands(g, torch.bfloat16)
+    cols = native.stage_im2col(x, k, k, (OH, OW), stride, pad, dil, native.OPERAND_BF16)
+    for splits in (2, 4):
+        ref = native.gemm_tc(cols, wt, 5, 10, False, 128, native.OPERAND_BF16, None, k=k * k * C, splits=splits)
+        got = native.gemm_conv(x_nhwc, wt, k, k, (OH, OW), stride, pad, dil, 5, 10, False, 128, native.OPERAND_BF16, splits=splits)
+        assert torch.equal(got, ref)
+
+
 def test_implicit_gemm_fp8_operands():
     g = (2, 128, 12, 12, 64, 3, 1, 1, 1)
     B, C, H, W, O, k, stride, pad, dil = g
@@ -91,7 +102,9 @@ def test_quant_conv_implicit_equals_staged_path(cfg, monkeypatch):
         outs.append((y.detach().clone(), x.grad.clone(), conv.weight.grad.clone(), fwd_launches))
     for a, b in zip(outs[0][:3], outs[1][:3]):
         assert torch.equal(a, b)
-    assert outs[1][3] == 2                                   # cast + GEMM
+    from cpd_b200.quant.functional import splits_for
+    oh = (12 + 2 * pad - (k - 1) - 1) // stride + 1
+    assert outs[1][3] == 2 + (splits_for(6 * oh * oh, cout, k * k * cin, 128) > 1)      # cast + GEMM (+ split-K fold)
 
 
 def _wgrad_operands(g):
