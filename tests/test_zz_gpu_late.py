@@ -163,3 +163,17 @@ def test_pipelined_input_prefetch_equals_plain_steps_on_gpu():
     torch.cuda.synchronize()
     assert plain == piped, (plain, piped)
     assert torch.equal(a.arena.model_flat, b.arena.model_flat)
+
+
+def test_implicit_gemm_tf32_operands():
+    from test_gpu_implicit_conv import _operands
+    g = (2, 32, 10, 10, 48, 3, 1, 1, 1)                     # 32 fp32 channels = one 128-byte block per tap
+    B, C, H, W, O, k, stride, pad, dil = g
+    x, w, _, _, (OH, OW) = _operands(g, torch.float32)
+    # operands through the staging kernel itself (it rounds fp32 to tf32 the way it does for the explicit matrix)
+    x_nhwc = native.stage_matrix(x.permute(0, 2, 3, 1).reshape(-1, C), native.OPERAND_TF32).view(B, H, W, C)
+    wt = native.stage_matrix(w.permute(0, 2, 3, 1).reshape(O, -1), native.OPERAND_TF32)
+    cols = native.stage_im2col(x, k, k, (OH, OW), stride, pad, dil, native.OPERAND_TF32)
+    ref = native.gemm_tc(cols, wt, 8, 23, False, 0, native.OPERAND_TF32, None, variant=native.GEMM_1CTA, k=k * k * C)
+    got = native.gemm_conv(x_nhwc, wt, k, k, (OH, OW), stride, pad, dil, 8, 23, False, 0, native.OPERAND_TF32, variant=native.GEMM_1CTA)
+    assert torch.equal(got, ref)
