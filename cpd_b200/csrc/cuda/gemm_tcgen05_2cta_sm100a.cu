@@ -31,7 +31,7 @@ using namespace tc;
 constexpr int CTA_M = 128, PAIR_M = 256, BLOCK_N = 256, CTA_BROWS = 128;
 constexpr int A_STAGE_BYTES = CTA_M * STAGE_ROW_BYTES;      // 16 KB
 constexpr int B_STAGE_BYTES = CTA_BROWS * STAGE_ROW_BYTES;  // 16 KB
-constexpr int NUM_STAGES = 7;
+constexpr int NUM_STAGES = 5;
 constexpr int NUM_ACC = 2;
 constexpr int TMEM_COLS = NUM_ACC * BLOCK_N;                // 512: all of TMEM
 constexpr int NUM_THREADS = 640;

@@ -46,7 +46,7 @@ namespace tc {
 constexpr int BLOCK_M = 128, BLOCK_N = 128;
 constexpr int A_STAGE_BYTES = BLOCK_M * STAGE_ROW_BYTES;  // 16 KB
 constexpr int B_STAGE_BYTES = BLOCK_N * STAGE_ROW_BYTES;  // 16 KB
-constexpr int NUM_STAGES = 7;                              // 7 x 32 KB in flight per SM: the kernels are TMA-latency bound (mbarrier spin in the MMA issuer)
+constexpr int NUM_STAGES = 4;                              // measured: 7 stages (all of shared memory) = +2.6 % with one requant at the end, -6 % with a requant every 256 (profiles/r2/t11_bench_gemm_7stages.json)
 constexpr int NUM_ACC = 2;                                // TMEM accumulator stages
 constexpr int TMEM_COLS = NUM_ACC * BLOCK_N;              // 256
 constexpr int NUM_THREADS = 640;
