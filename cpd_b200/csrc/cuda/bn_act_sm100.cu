@@ -66,36 +66,51 @@ __device__ __forceinline__ void reduce_rows(float4& a, float4& b, int lanes, int
   __syncthreads();
 }
 
-// Last CTA of a channel tile: reduce the [slabs][2][C] partials of the tile's channels in a FIXED order, with the whole
-// block (a serial per-channel loop over ~600 slabs cost ~20 us of dependent L2 round trips per launch: 40 launches a
-// step).  Thread (lane, g) sums slabs g, g + G, g + 2G, ... of its 4 channels with independent vector loads; the G group
-// sums are then combined in group order.  Result: sum / sumsq per channel in shared memory (double).
-__device__ __forceinline__ void reduce_partials(const float* __restrict__ part, int slabs, int C, int lanes, double* s_sum, double* s_sq,
-                                                double4* scratch) {
+// Deterministic two-level reduction of the per-slab partial sums.  The single "last CTA reduces all ~600 slabs" of the
+// first version was the tail of every statistics launch: ~75 dependent-ish L2 loads per thread while 147 SMs idle
+// (ncu r2t7: 23 us of SM activity inside a 42 us kernel).  Now the slabs form groups of kBnGroup; the LAST CTA of a
+// group to arrive folds that group's partials (one batch of loads) into a double-precision group partial, and the last
+// group to finish folds the <= 37 group partials.  Every sum runs in a fixed order (slab order inside a group, group
+// order across groups), whichever CTA happens to execute it: bitwise reproducible.
+constexpr int kBnGroup = 16;
+
+__device__ __forceinline__ double4 ldcg_d4(const double* p) {
+  const double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ double4 ldcg_as_d4(const float* p) {
+  const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+  return make_double4(v.x, v.y, v.z, v.w);
+}
+__device__ __forceinline__ double4 ldcg_as_d4(const double* p) { return ldcg_d4(p); }
+
+// entries [first, first + count) of src[.][2][C] (float or double) -> per-channel sums in a / b of the g == 0 threads:
+// thread (lane, g) adds entries g, g + G, ... (4 in flight), the G partial sums are then combined in g order
+template <typename T>
+__device__ __forceinline__ void reduce_entries(const T* __restrict__ src, int first, int count, int C, int lanes, double4& a, double4& b,
+                                               double4* scratch) {
   const int G = kBnThreads / lanes;
   const int lane = threadIdx.x % lanes, g = threadIdx.x / lanes;
   const int c0 = (blockIdx.x * lanes + lane) * 4;
-  double4 a = make_double4(0.0, 0.0, 0.0, 0.0), b = a;
+  a = make_double4(0.0, 0.0, 0.0, 0.0); b = a;
   if (c0 < C) {
-    // 8 slabs' partials (16 independent L2 loads) in flight per thread, then added in slab order: the loop is a chain of
-    // L2 round trips otherwise (~37 of them for 592 slabs: the tail of every statistics launch)
-    int sl = g;
-    for (; sl + 7 * G < slabs; sl += 8 * G) {
-      float4 u[8], v[8];
+    int e = g;
+    for (; e + 3 * G < count; e += 4 * G) {
+      double4 u[4], v[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        u[j] = __ldcg(reinterpret_cast<const float4*>(part + ((long long)(sl + j * G) * 2 + 0) * C + c0));     // other SMs wrote these
-        v[j] = __ldcg(reinterpret_cast<const float4*>(part + ((long long)(sl + j * G) * 2 + 1) * C + c0));
+      for (int j = 0; j < 4; ++j) {
+        u[j] = ldcg_as_d4(src + ((long long)(first + e + j * G) * 2 + 0) * C + c0);     // other SMs wrote these
+        v[j] = ldcg_as_d4(src + ((long long)(first + e + j * G) * 2 + 1) * C + c0);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
         a.x += u[j].x; a.y += u[j].y; a.z += u[j].z; a.w += u[j].w;
         b.x += v[j].x; b.y += v[j].y; b.z += v[j].z; b.w += v[j].w;
       }
     }
-    for (; sl < slabs; sl += G) {
-      const float4 u = __ldcg(reinterpret_cast<const float4*>(part + ((long long)sl * 2 + 0) * C + c0));
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + ((long long)sl * 2 + 1) * C + c0));
+    for (; e < count; e += G) {
+      const double4 u = ldcg_as_d4(src + ((long long)(first + e) * 2 + 0) * C + c0);
+      const double4 v = ldcg_as_d4(src + ((long long)(first + e) * 2 + 1) * C + c0);
       a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
       b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
     }
@@ -109,10 +124,58 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ part, 
       a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
       b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
     }
+  }
+  __syncthreads();
+}
+
+// Called by every CTA after it wrote part[blockIdx.y].  Returns true in exactly one CTA per channel tile - the one that
+// finishes the reduction - with the per-channel totals in s_sum / s_sq (shared, double).
+// counters (per channel tile): [0] groups finished, [1 + grp] slabs of group grp arrived; all return to 0.
+__device__ __forceinline__ bool arrive_and_reduce(const float* __restrict__ part, double* __restrict__ gpart, unsigned* __restrict__ counters,
+                                                  int C, int lanes, double* s_sum, double* s_sq, double4* scratch) {
+  __shared__ bool last;
+  const int slabs = (int)gridDim.y, groups = (slabs + kBnGroup - 1) / kBnGroup;
+  const int grp = (int)blockIdx.y / kBnGroup;
+  const int gfirst = grp * kBnGroup, gcount = min(kBnGroup, slabs - gfirst);
+  unsigned* cnt = counters + (long long)blockIdx.x * (1 + groups);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&cnt[1 + grp], 1u);
+    last = done == (unsigned)gcount - 1u;
+    if (last) cnt[1 + grp] = 0u;                                // ready for the next launch / graph replay
+  }
+  __syncthreads();
+  if (!last) return false;
+  __threadfence();
+  const int lane = threadIdx.x % lanes, g = threadIdx.x / lanes;
+  const int c0 = (blockIdx.x * lanes + lane) * 4;
+  double4 a, b;
+  reduce_entries(part, gfirst, gcount, C, lanes, a, b, scratch);
+  if (groups > 1) {
+    if (g == 0 && c0 < C) {
+      double* o = gpart + ((long long)grp * 2) * C + c0;
+      *reinterpret_cast<double2*>(o) = make_double2(a.x, a.y); *reinterpret_cast<double2*>(o + 2) = make_double2(a.z, a.w);
+      *reinterpret_cast<double2*>(o + C) = make_double2(b.x, b.y); *reinterpret_cast<double2*>(o + C + 2) = make_double2(b.z, b.w);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned done = atomicAdd(&cnt[0], 1u);
+      last = done == (unsigned)groups - 1u;
+      if (last) cnt[0] = 0u;
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+    reduce_entries(gpart, 0, groups, C, lanes, a, b, scratch);
+  }
+  if (g == 0 && c0 < C) {
     s_sum[lane * 4 + 0] = a.x; s_sum[lane * 4 + 1] = a.y; s_sum[lane * 4 + 2] = a.z; s_sum[lane * 4 + 3] = a.w;
     s_sq[lane * 4 + 0] = b.x; s_sq[lane * 4 + 1] = b.y; s_sq[lane * 4 + 2] = b.z; s_sq[lane * 4 + 3] = b.w;
   }
   __syncthreads();
+  return true;
 }
 
 // ---- forward: statistics ------------------------------------------------------------------------------------------
@@ -121,10 +184,9 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_stats_kernel(const float* __restrict__ x, long long M, int C, long long rows_per_slab, int lanes,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ running_mean,
                 float* __restrict__ running_var, float momentum, float eps, float* __restrict__ part,
-                unsigned* __restrict__ counters, float* __restrict__ mean, float* __restrict__ rstd,
+                double* __restrict__ gpart, unsigned* __restrict__ counters, float* __restrict__ mean, float* __restrict__ rstd,
                 float* __restrict__ scale, float* __restrict__ bias, long long* __restrict__ num_batches_tracked) {
   __shared__ float4 sm[2 * kBnThreads];
-  __shared__ bool last;
   const int rows_par = kBnThreads / lanes;
   const int lane = threadIdx.x % lanes, ty = threadIdx.x / lanes;
   const int c0 = (blockIdx.x * lanes + lane) * 4;
@@ -162,21 +224,11 @@ bn_stats_kernel(const float* __restrict__ x, long long M, int C, long long rows_
     *reinterpret_cast<float4*>(part + ((long long)blockIdx.y * 2 + 0) * C + c0) = s;
     *reinterpret_cast<float4*>(part + ((long long)blockIdx.y * 2 + 1) * C + c0) = q;
   }
-  // last CTA of this channel tile: fixed-order reduction of the slab partials
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned done = atomicAdd(&counters[blockIdx.x], 1u);
-    last = done == gridDim.y - 1;
-    if (last) counters[blockIdx.x] = 0u;                        // ready for the next launch / graph replay
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;     // nn.BatchNorm2d's counter
+  // fixed-order two-level reduction of the slab partials; one CTA per channel tile comes out with the totals
   __shared__ double s_sum[128], s_sq[128];
   __shared__ double4 scratch[2 * kBnThreads];
-  reduce_partials(part, (int)gridDim.y, C, lanes, s_sum, s_sq, scratch);
+  if (!arrive_and_reduce(part, gpart, counters, C, lanes, s_sum, s_sq, scratch)) return;
+  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;     // nn.BatchNorm2d's counter
   const int nch = lanes * 4;
   for (int i = threadIdx.x; i < nch; i += kBnThreads) {
     const int c = blockIdx.x * nch + i;
@@ -249,10 +301,9 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ y, const unsigned* __restrict__ mask,
                     const float* __restrict__ x, long long M, int C,
                     long long rows_per_slab, int lanes, const float* __restrict__ mean, const float* __restrict__ rstd,
-                    float* __restrict__ part, unsigned* __restrict__ counters, float* __restrict__ dgamma,
+                    float* __restrict__ part, double* __restrict__ gpart, unsigned* __restrict__ counters, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2) {
   __shared__ float4 sm[2 * kBnThreads];
-  __shared__ bool last;
   const int rows_par = kBnThreads / lanes;
   const int lane = threadIdx.x % lanes, ty = threadIdx.x / lanes;
   const int c0 = (blockIdx.x * lanes + lane) * 4;
@@ -303,19 +354,9 @@ bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ y, c
     *reinterpret_cast<float4*>(part + ((long long)blockIdx.y * 2 + 0) * C + c0) = s;
     *reinterpret_cast<float4*>(part + ((long long)blockIdx.y * 2 + 1) * C + c0) = q;
   }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned done = atomicAdd(&counters[blockIdx.x], 1u);
-    last = done == gridDim.y - 1;
-    if (last) counters[blockIdx.x] = 0u;
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
   __shared__ double s_sum[128], s_sq[128];
   __shared__ double4 scratch[2 * kBnThreads];
-  reduce_partials(part, (int)gridDim.y, C, lanes, s_sum, s_sq, scratch);
+  if (!arrive_and_reduce(part, gpart, counters, C, lanes, s_sum, s_sq, scratch)) return;
   const int nch = lanes * 4;
   for (int i = threadIdx.x; i < nch; i += kBnThreads) {
     const int c = blockIdx.x * nch + i;
@@ -368,10 +409,26 @@ int ew_grid(long long n4, int sms) {
 
 }  // namespace
 
-// workspace: float part[slabs_max * 2 * C] + unsigned counters[ctiles]; stats: float[4 * C] = mean | rstd | scale | bias
+// workspace: unsigned counters[kBnCounters] | double gpart[groups * 2 * C] | float part[slabs * 2 * C].  The counters sit at a
+// FIXED offset: they are the only part that must be zero between launches (the kernels re-arm them), so one zero-
+// initialised buffer serves any batch size - the last, smaller batch of an epoch uses a different slab geometry.
+// stats: float[4 * C] = mean | rstd | scale | bias
+constexpr int kBnCounters = 1024;
+struct BnWs { float* part; double* gpart; unsigned* counters; };
+inline int bn_ws_groups(const BnGeom& g) { return (g.slabs + kBnGroup - 1) / kBnGroup; }
+inline BnWs bn_ws(float* workspace, const BnGeom& g, int C) {
+  BnWs w;
+  w.counters = reinterpret_cast<unsigned*>(workspace);
+  w.gpart = reinterpret_cast<double*>(workspace + kBnCounters);
+  w.part = reinterpret_cast<float*>(w.gpart + (long long)bn_ws_groups(g) * 2 * C);
+  return w;
+}
+inline bool bn_ws_ok(const float* workspace, const BnGeom& g) {
+  return !(reinterpret_cast<uintptr_t>(workspace) & 7u) && (long long)g.ctiles * (1 + bn_ws_groups(g)) <= kBnCounters;
+}
 long long bn_workspace_floats(long long M, int C) {
   const BnGeom g = bn_geom(M, C, device_sm_count(-1));
-  return (long long)g.slabs * 2 * C + g.ctiles + 8;
+  return kBnCounters + 2LL * bn_ws_groups(g) * 2 * C + (long long)g.slabs * 2 * C + 8;
 }
 
 int bn_act_forward_cuda(const float* x, const float* res, float* y, long long M, int C, const float* gamma, const float* beta,
@@ -381,11 +438,13 @@ int bn_act_forward_cuda(const float* x, const float* res, float* y, long long M,
   if (C % 4) return -1;
   const int sms = device_sm_count(-1);
   const BnGeom g = bn_geom(M, C, sms);
-  float* part = workspace;
-  unsigned* counters = reinterpret_cast<unsigned*>(workspace + (long long)g.slabs * 2 * C);
+  if (!bn_ws_ok(workspace, g)) return -3;
+  const BnWs w = bn_ws(workspace, g, C);
+  float* part = w.part;
+  unsigned* counters = w.counters;
   float *mean = stats, *rstd = stats + C, *scale = stats + 2 * C, *bias = stats + 3 * C;
   bn_stats_kernel<<<dim3(g.ctiles, g.slabs), kBnThreads, 0, st>>>(x, M, C, g.rows_per_slab, g.lanes, gamma, beta, running_mean, running_var,
-                                                                   momentum, eps, part, counters, mean, rstd, scale, bias,
+                                                                   momentum, eps, part, w.gpart, counters, mean, rstd, scale, bias,
                                                                    num_batches_tracked);
   const long long n4 = M * C / 4;
   if (relu_mask && (n4 % 8)) return -2;                  // the bitmask path packs 8 vectors per word
@@ -404,16 +463,18 @@ int bn_act_backward_cuda(const float* dy, const float* y, const unsigned* relu_m
   if (C % 4) return -1;
   const int sms = device_sm_count(-1);
   const BnGeom g = bn_geom(M, C, sms);
-  float* part = workspace;
-  unsigned* counters = reinterpret_cast<unsigned*>(workspace + (long long)g.slabs * 2 * C);
+  if (!bn_ws_ok(workspace, g)) return -3;
+  const BnWs w = bn_ws(workspace, g, C);
+  float* part = w.part;
+  unsigned* counters = w.counters;
   const float *mean = stats, *rstd = stats + C;
   float *dgamma = grads, *dbeta = grads + C, *c1 = grads + 2 * C, *c2 = grads + 3 * C;
   if (relu)
     bn_bwd_stats_kernel<true><<<dim3(g.ctiles, g.slabs), kBnThreads, 0, st>>>(dy, y, relu_mask, x, M, C, g.rows_per_slab, g.lanes, mean, rstd, part,
-                                                                                counters, dgamma, dbeta, c1, c2);
+                                                                                w.gpart, counters, dgamma, dbeta, c1, c2);
   else
     bn_bwd_stats_kernel<false><<<dim3(g.ctiles, g.slabs), kBnThreads, 0, st>>>(dy, y, nullptr, x, M, C, g.rows_per_slab, g.lanes, mean, rstd, part,
-                                                                                 counters, dgamma, dbeta, c1, c2);
+                                                                                 w.gpart, counters, dgamma, dbeta, c1, c2);
   const long long n4 = M * C / 4;
   const int grid = ew_grid(n4, sms);
   if (relu && dres) bn_bwd_apply_kernel<true, true><<<grid, kBnThreads, 0, st>>>(dy, y, relu_mask, x, dx, dres, n4, C / 4, mean, rstd, gamma, c1, c2);

@@ -177,3 +177,43 @@ def test_implicit_gemm_tf32_operands():
     ref = native.gemm_tc(cols, wt, 8, 23, False, 0, native.OPERAND_TF32, None, variant=native.GEMM_1CTA, k=k * k * C)
     got = native.gemm_conv(x_nhwc, wt, k, k, (OH, OW), stride, pad, dil, 8, 23, False, 0, native.OPERAND_TF32, variant=native.GEMM_1CTA)
     assert torch.equal(got, ref)
+
+
+def test_fused_bn_survives_a_change_of_batch_size():
+    """The last batch of an epoch is smaller: another slab geometry over the SAME workspace.  The arrival counters live at
+    a fixed offset, so stale partial sums of the bigger launch can never be read as counters (they could, before)."""
+    import torch.nn.functional as F
+    from cpd_b200.nn import BatchNormAct2d
+    torch.manual_seed(0)
+    C = 64
+    fused = BatchNormAct2d(C, relu=True).cuda()
+    stock = torch.nn.BatchNorm2d(C).cuda()
+    stock.load_state_dict(fused.state_dict())
+    for B in (64, 7, 64, 3, 33):
+        x = torch.randn(B, C, 16, 16, device="cuda").contiguous(memory_format=torch.channels_last)
+        xf, xs = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        y, ys = fused(xf), F.relu(stock(xs))
+        assert torch.allclose(y, ys, rtol=1e-4, atol=1e-4), (B, float((y - ys).abs().max()))
+        dy = torch.randn_like(ys)
+        y.backward(dy); ys.backward(dy)
+        assert torch.allclose(xf.grad, xs.grad, rtol=1e-3, atol=2e-4 * float(xs.grad.abs().max())), B
+        assert torch.allclose(fused.running_mean, stock.running_mean, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(fused.running_var, stock.running_var, rtol=1e-4, atol=1e-5)
+
+
+def test_fused_bn_statistics_are_bitwise_reproducible():
+    """Two-level reduction of the slab partials: whichever CTAs arrive last, every sum runs in a fixed order."""
+    from cpd_b200.nn import BatchNormAct2d
+    torch.manual_seed(1)
+    x = torch.randn(128, 64, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+    dy = torch.randn_like(x)
+    outs = []
+    for _ in range(4):
+        bn = BatchNormAct2d(64, relu=True).cuda()
+        xi = x.clone().requires_grad_(True)
+        y = bn(xi)
+        y.backward(dy)
+        outs.append((y.detach().clone(), xi.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone(), bn.running_var.clone()))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert torch.equal(a, b)
