@@ -62,3 +62,29 @@ def test_resnet50_main_trainer_runs_and_auto_resumes(tmp_path):
     out2 = _run(base + ["--max-iter", "6"], str(tmp_path))            # resume="auto": picks up the newest checkpoint
     assert "=> resumed from" in out2 and "at iteration 4" in out2 and " * All Loss" in out2
     assert os.path.isfile(str(tmp_path / "ck" / "ckpt_6.pth"))
+
+
+@pytest.mark.timeout(900)
+def test_fcn_segmentation_trainer_runs_through_the_optimizer_hook(tmp_path):
+    """The reference's FCN/Cityscapes workload (mmcv-fork optimizer hook, README.md:132-151): runner + APSOptimizerHook."""
+    out = _run([os.path.join(ROOT, "examples/FCN/train_fcn.py"), "--cpu", "--arch", "fcn_r18_d8", "--width", "8", "--crop", "65",
+                "--batch-size", "2", "--max-iters", "6", "--dataset-len", "8", "--val-len", "4", "--val-freq", "3", "--print-freq", "2",
+                "--workers", "0", "--use_APS", "--use_kahan", "--grad-clip", "5"], str(tmp_path))
+    assert "Iter [6/6]" in out and out.count(" * Iter") == 2 and "nan" not in out.lower()
+    assert "lr 0.00207" in out                                   # poly schedule: (0.01 - 1e-4) * (1 - 5/6)^0.9 + 1e-4
+
+
+def test_fcn_d8_topology():
+    import torch
+    from cpd_b200.models import create_model
+    m = create_model("fcn_r50_d8")
+    assert sum(p.numel() for p in m.parameters()) == 35_320_678       # ResNet-50 backbone + FCN head (512) + aux head (256), 19 classes
+    small = create_model("fcn_r18_d8", width=8).eval()
+    feats = []
+    hooks = [st.register_forward_hook(lambda _m, _i, o: feats.append(o.shape[-1])) for st in small.stages]
+    with torch.no_grad():
+        y = small(torch.randn(1, 3, 129, 129))
+    for h in hooks:
+        h.remove()
+    assert y.shape == (1, 19, 129, 129)
+    assert feats == [33, 17, 17, 17]                                   # output stride 8: stages 3 and 4 dilate instead of striding
