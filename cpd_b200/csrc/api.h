@@ -145,11 +145,7 @@ int bn_act_backward_cuda(const float* dy, const float* y, const unsigned* relu_m
 struct ConvGeom {
   int B, H, W, C;               // activation tensor [B, H, W, C], C contiguous
   int KH, KW, OH, OW;
-  int stride, pad, dil;         // pad: rows of zero above the image (and left of it when pad_w < 0)
-  int pad_w = -1;               // >= 0: a different left padding.  Bottom / right padding is whatever OH / OW imply.
-  // sc_stride > 0: OUTPUT SCATTER - GEMM row (n, i, j) is stored at row (n * sc_H + i * sc_stride + sc_a) * sc_W + j * sc_stride + sc_b
-  // of C: one parity class of a strided convolution's data gradient writes its pixels of dx in place.
-  int sc_stride = 0, sc_a = 0, sc_b = 0, sc_H = 0, sc_W = 0;
+  int stride, pad, dil;
 };
 int gemm_tc_cuda(const void* A, const void* B, float* C, int M, int N, int K, int e, int m,
                  bool kahan, int k_slice, int operand_mode, const float* bias, int variant, cudaStream_t st,

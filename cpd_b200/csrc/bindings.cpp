@@ -101,12 +101,8 @@ PYBIND11_MODULE(_C, m) {
   m.def("gemm_conv_cuda", [](uptr X, uptr Bt, uptr C, int N, std::vector<int> geom, int e, int mb, bool kahan, int k_slice,
                              int operand_mode, uptr bias, int variant, uptr stream, int64_t ldb, int splits, uptr workspace) {
     check_fmt(e, mb);
-    if (geom.size() != 11 && geom.size() != 17)
-      throw std::invalid_argument("gemm_conv: geom = (B, H, W, C, KH, KW, OH, OW, stride, pad, dil[, pad_w, sc_stride, sc_a, sc_b, sc_H, sc_W])");
+    if (geom.size() != 11) throw std::invalid_argument("gemm_conv: geom = (B, H, W, C, KH, KW, OH, OW, stride, pad, dil)");
     cpd::ConvGeom g{geom[0], geom[1], geom[2], geom[3], geom[4], geom[5], geom[6], geom[7], geom[8], geom[9], geom[10]};
-    if (geom.size() == 17) {
-      g.pad_w = geom[11]; g.sc_stride = geom[12]; g.sc_a = geom[13]; g.sc_b = geom[14]; g.sc_H = geom[15]; g.sc_W = geom[16];
-    }
     const long long M = (long long)g.B * g.OH * g.OW, K = (long long)g.KH * g.KW * g.C;
     if (M > INT32_MAX || K > INT32_MAX) throw std::invalid_argument("gemm_conv: problem too large");
     int rc = cpd::gemm_tc_cuda(P<const void>(X), P<const void>(Bt), P<float>(C), (int)M, N, (int)K, e, mb, kahan, k_slice, operand_mode,

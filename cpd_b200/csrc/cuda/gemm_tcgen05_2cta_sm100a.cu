@@ -136,7 +136,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           cn = m0 / conv.OHW;
           const int rem = m0 - cn * conv.OHW, p = rem / conv.OW;
           ch = p * conv.stride - conv.pad;
-          cw = (rem - p * conv.OW) * conv.stride - conv.pad_w;
+          cw = (rem - p * conv.OW) * conv.stride - conv.pad;
         }
         for (int kb = 0; kb < num_kblocks; ++kb, ++it) {
           const int s = it % NUM_STAGES;
@@ -371,7 +371,7 @@ int gemm_tc2_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, 
     default: return -1;
   }
   if (conv) {
-    if (conv->sc_stride || !conv_geom_ok(*conv, elem_bytes, M, K)) return -7;
+    if (!conv_geom_ok(*conv, elem_bytes, M, K)) return -7;
     lda = K;
   }
   if ((lda * elem_bytes) % 16 != 0 || (ldb * elem_bytes) % 16 != 0) return -2;

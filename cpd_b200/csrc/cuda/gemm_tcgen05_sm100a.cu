@@ -125,7 +125,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           cn = m0 / conv.OHW;
           const int rem = m0 - cn * conv.OHW, p = rem / conv.OW;
           ch = p * conv.stride - conv.pad;
-          cw = (rem - p * conv.OW) * conv.stride - conv.pad_w;
+          cw = (rem - p * conv.OW) * conv.stride - conv.pad;
         }
         for (int kb = 0; kb < num_kblocks; ++kb, ++it) {
           const int s = it % NUM_STAGES;
@@ -135,7 +135,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (conv.wgrad) {
             const int pix0 = (kb0 + kb) * 64;                        // K-block = 64 output positions
             const int pn = pix0 / conv.OHW, rem = pix0 - pn * conv.OHW, pp = rem / conv.OW;
-            const int ph_ = pp * conv.stride - conv.pad, pw_ = (rem - pp * conv.OW) * conv.stride - conv.pad_w;
+            const int ph_ = pp * conv.stride - conv.pad, pw_ = (rem - pp * conv.OW) * conv.stride - conv.pad;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               tma_load_2d(smem_a + s * A_STAGE_BYTES + j * (A_STAGE_BYTES / 2), &tmap_a, &bars->full[s], m0 + 64 * j, pix0);
@@ -244,12 +244,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int gm = m0 + row;
       const int gn = n0 + cg * EPI_COLS;
       if (gm < M && gn < N) {
-        long long orow = gm;
-        if (conv.sc_stride) {                              // one parity class of a strided data gradient: pixel (n, i, j) of the class
-          const int n = gm / conv.OHW, rem = gm - n * conv.OHW, i = rem / conv.OW;
-          orow = ((long long)n * conv.sc_H + i * conv.sc_stride + conv.sc_a) * conv.sc_W + (rem - i * conv.OW) * conv.sc_stride + conv.sc_b;
-        }
-        float* crow = Ct + orow * N + gn;
+        float* crow = Ct + (long long)gm * N + gn;
         const int ncols = min(EPI_COLS, N - gn);
         if (ncols == EPI_COLS && (N & 3) == 0) {
 #pragma unroll
@@ -327,10 +322,8 @@ bool make_tmap_im2col(CUtensorMap* tm, const void* base, const ConvGeom& g, int 
   }
   cuuint64_t gdim[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
   cuuint64_t gstride[3] = {(cuuint64_t)g.C * elem_bytes, (cuuint64_t)g.W * g.C * elem_bytes, (cuuint64_t)g.H * g.W * g.C * elem_bytes};
-  const int pad_w = g.pad_w >= 0 ? g.pad_w : g.pad;
-  int lower[2] = {-pad_w, -g.pad};
-  // the box holds EXACTLY OW x OH base pixels: (IN + upper - lower - 1) / stride + 1 == OUT
-  int upper[2] = {(g.OW - 1) * g.stride + 1 - g.W + lower[0], (g.OH - 1) * g.stride + 1 - g.H + lower[1]};
+  int lower[2] = {-g.pad, -g.pad};
+  int upper[2] = {g.pad - (g.KW - 1) * g.dil, g.pad - (g.KH - 1) * g.dil};
   cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
   return enc(tm, dt, 4, const_cast<void*>(base), gdim, gstride, lower, upper, (cuuint32_t)(tc::STAGE_ROW_BYTES / elem_bytes),
              (cuuint32_t)box_pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -340,25 +333,20 @@ bool make_tmap_im2col(CUtensorMap* tm, const void* base, const ConvGeom& g, int 
 // does the implicit-GEMM path cover this convolution?  (corner / offset ranges of the descriptor, whole channel blocks)
 bool conv_geom_ok(const ConvGeom& g, int elem_bytes, int M, int K) {
   const int cpb = tc::STAGE_ROW_BYTES / elem_bytes;
-  const int pad_w = g.pad_w >= 0 ? g.pad_w : g.pad;
   if (g.C <= 0 || g.C % cpb) return false;
-  if (g.stride < 1 || g.stride > 8 || g.dil < 1 || g.pad < 0 || g.pad > 127 || pad_w > 127) return false;
+  if (g.stride < 1 || g.stride > 8 || g.dil < 1 || g.pad < 0 || g.pad > 127) return false;
   if ((g.KH - 1) * g.dil > 255 || (g.KW - 1) * g.dil > 255) return false;
-  if (g.OH < 1 || g.OW < 1 || g.KH < 1 || g.KW < 1) return false;
-  const int up_w = (g.OW - 1) * g.stride + 1 - g.W - pad_w, up_h = (g.OH - 1) * g.stride + 1 - g.H - g.pad;
-  if (up_w < -128 || up_w > 127 || up_h < -128 || up_h > 127) return false;
-  if (g.sc_stride && (g.sc_stride < 1 || g.sc_a < 0 || g.sc_b < 0 || (g.OH - 1) * g.sc_stride + g.sc_a >= g.sc_H ||
-                      (g.OW - 1) * g.sc_stride + g.sc_b >= g.sc_W)) return false;
+  if (g.pad - (g.KW - 1) * g.dil < -128 || g.pad - (g.KH - 1) * g.dil < -128) return false;
+  if (g.OH != (g.H + 2 * g.pad - g.dil * (g.KH - 1) - 1) / g.stride + 1 || g.OW != (g.W + 2 * g.pad - g.dil * (g.KW - 1) - 1) / g.stride + 1) return false;
+  if (g.OH < 1 || g.OW < 1) return false;
   return (long long)g.B * g.OH * g.OW == M && (long long)g.KH * g.KW * g.C == K;
 }
 
 tc::ConvA conv_device_geom(const ConvGeom* g, int elem_bytes) {
-  tc::ConvA c = {0, 1, 1, 1, 0, 1, 1, 0, 1, 1, 8192, 1024, 0, 0, 0, 0, 0, 0};
+  tc::ConvA c = {0, 1, 1, 1, 0, 1, 1, 0, 1, 1, 8192, 1024};
   if (g) {
     c.cblocks = g->C / (tc::STAGE_ROW_BYTES / elem_bytes);
     c.OHW = g->OH * g->OW; c.OW = g->OW; c.stride = g->stride; c.pad = g->pad; c.dil = g->dil; c.KW = g->KW;
-    c.pad_w = g->pad_w >= 0 ? g->pad_w : g->pad;
-    c.sc_stride = g->sc_stride; c.sc_a = g->sc_a; c.sc_b = g->sc_b; c.sc_H = g->sc_H; c.sc_W = g->sc_W;
   }
   return c;
 }
@@ -427,10 +415,6 @@ int gemm_tc_cuda(const void* A, const void* Bt, float* C, int M, int N, int K, i
   if (splits > 1 && !workspace) return -6;
   // CTA-pair kernel when it covers the format and its 256x256 tiles still fill the machine
   // (Kahan's four casts per element make the kernel requant-bound either way; measured slightly faster on 128x128 tiles)
-  if (conv && conv->sc_stride) {                         // the scattering epilogue lives in the 128x128 kernel
-    if (splits > 1 || variant == 2) return -8;
-    variant = 1;
-  }
   if (splits == 1 && (variant == 2 || (variant == 0 && !kahan && 2 * ((M + 255) / 256) * ((N + 255) / 256) >= device_sm_count(-1)))) {
     const int rc = gemm_tc2_cuda(A, Bt, C, M, N, K, e, m, kahan, k_slice, operand_mode, bias, st, lda, ldb, conv);
     if (rc == 0 || variant == 2) return rc;

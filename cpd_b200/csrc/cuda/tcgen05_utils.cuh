@@ -68,8 +68,6 @@ struct ConvA {
   int stride, pad, dil, KW;
   int wgrad, C, taps; // weight-gradient mode, channels, KH * KW
   int lbo, sbo;       // MN-major descriptor strides in bytes (wgrad mode)
-  int pad_w;          // left padding (pad = top padding)
-  int sc_stride, sc_a, sc_b, sc_H, sc_W;   // output scatter (ConvGeom), 0 = rows stored in GEMM order
 };
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, int lbo, int sbo) {
   uint64_t d = 0;

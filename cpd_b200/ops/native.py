@@ -191,16 +191,13 @@ def conv_implicit_ok(C: int, kh: int, kw: int, stride: int, pad: int, dil: int, 
             (kw - 1) * dil <= 255 and pad - (kh - 1) * dil >= -128 and pad - (kw - 1) * dil >= -128)
 
 
-def gemm_conv(x_nhwc: torch.Tensor, bt: torch.Tensor, kh: int, kw: int, out_hw, stride: int, pad, dil: int, exp: int, man: int,
+def gemm_conv(x_nhwc: torch.Tensor, bt: torch.Tensor, kh: int, kw: int, out_hw, stride: int, pad: int, dil: int, exp: int, man: int,
               kahan: bool = False, k_slice: int = 128, operand_mode: int = OPERAND_BF16, bias: Optional[torch.Tensor] = None,
-              variant: int = GEMM_AUTO, splits: int = 1, out: Optional[torch.Tensor] = None, scatter=None) -> torch.Tensor:
+              variant: int = GEMM_AUTO, splits: int = 1) -> torch.Tensor:
     """Implicit-GEMM convolution on tcgen05: y[(b,oh,ow), o] = sum_(kh,kw,c) x[b, oh*s-p+kh*d, ow*s-p+kw*d, c] * bt[o, (kh,kw,c)].
     ``x_nhwc`` is the dense [B, H, W, C] activation tensor ALREADY in the operand dtype; the im2col matrix is never
     written: the kernel's TMA producer reads the taps straight from it (im2col-mode tensor map, zero-filled halo).
-    ``bt`` [O, >= KH*KW*C] K-major filter matrix.  Accumulator re-quantised to (exp, man) every ``k_slice``.
-    ``pad``: int, or (top, left) when they differ (bottom / right padding is whatever ``out_hw`` implies).
-    ``scatter=(s, a, b, H, W)`` with ``out`` [B*H*W, O]: output pixel (n, i, j) is stored at pixel (n, s*i + a, s*j + b) of
-    ``out`` - how the parity classes of a strided convolution's data gradient write dx in place."""
+    ``bt`` [O, >= KH*KW*C] K-major filter matrix.  Accumulator re-quantised to (exp, man) every ``k_slice``."""
     _check_fmt(exp, man)
     want = _OPERAND_TORCH[operand_mode]
     if not (x_nhwc.is_cuda and x_nhwc.dim() == 4 and x_nhwc.is_contiguous() and x_nhwc.dtype == want):
@@ -210,27 +207,14 @@ def gemm_conv(x_nhwc: torch.Tensor, bt: torch.Tensor, kh: int, kw: int, out_hw, 
     K = kh * kw * C
     if not (bt.is_cuda and bt.dim() == 2 and bt.stride(1) == 1 and bt.dtype == want and bt.shape[1] >= K):
         raise ValueError("gemm_conv: K-major filter matrix [O, KH*KW*C] in the operand dtype expected")
-    pad_h, pad_w = (int(pad[0]), int(pad[1])) if isinstance(pad, (tuple, list)) else (int(pad), int(pad))
-    if not (conv_implicit_ok(C, kh, kw, stride, pad_h, dil, operand_mode) and conv_implicit_ok(C, kh, kw, stride, pad_w, dil, operand_mode)):
+    if not conv_implicit_ok(C, kh, kw, stride, pad, dil, operand_mode):
         raise ValueError("gemm_conv: convolution not covered by the implicit-GEMM path (see conv_implicit_ok)")
     O = bt.shape[0]
+    out = torch.empty(B * OH * OW, O, dtype=torch.float32, device=x_nhwc.device)
     splits = max(1, int(splits))
-    geom = [B, H, W, C, kh, kw, OH, OW, stride, pad_h, dil]
-    if scatter is not None:
-        s_, a_, b_, SH, SW = [int(v) for v in scatter]
-        if out is None or out.shape != (B * SH * SW, O) or not out.is_contiguous() or out.dtype != torch.float32 or splits != 1 or bias is not None:
-            raise ValueError("gemm_conv: scatter needs out = fp32 [B*H*W, O], no split-K, no bias")
-        geom += [pad_w, s_, a_, b_, SH, SW]
-    else:
-        if pad_w != pad_h:
-            geom += [pad_w, 0, 0, 0, 0, 0]
-        if out is None:
-            out = torch.empty(B * OH * OW, O, dtype=torch.float32, device=x_nhwc.device)
-        elif out.shape != (B * OH * OW, O) or not out.is_contiguous() or out.dtype != torch.float32:
-            raise ValueError("gemm_conv: out must be fp32 [B*OH*OW, O]")
     ws = torch.empty(splits, B * OH * OW, O, dtype=torch.float32, device=x_nhwc.device) if splits > 1 else None
     with torch.cuda.device(x_nhwc.device):
-        rc = _C.gemm_conv_cuda(x_nhwc.data_ptr(), bt.data_ptr(), out.data_ptr(), O, geom,
+        rc = _C.gemm_conv_cuda(x_nhwc.data_ptr(), bt.data_ptr(), out.data_ptr(), O, [B, H, W, C, kh, kw, OH, OW, stride, pad, dil],
                                int(exp), int(man), bool(kahan), int(k_slice), int(operand_mode), _ptr(bias), int(variant),
                                _stream(x_nhwc), int(bt.stride(0) if O > 1 else bt.shape[1]), splits, _ptr(ws))
     if rc != 0:

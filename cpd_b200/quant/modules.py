@@ -71,20 +71,6 @@ class Quant_LinearFunction(Function):
 
 
 _IMPLICIT = os.environ.get("CPD_B200_CONV_IMPLICIT", "1") != "0"       # implicit-GEMM (im2col-mode TMA) convolutions where covered
-_PARITY = os.environ.get("CPD_B200_DGRAD_PARITY", "0") != "0"          # strided data gradient as stride^2 implicit GEMMs (no zero-upsampled im2col)
-
-
-def _parity_classes(K: int, stride: int, pad: int):
-    """Data gradient of a stride-s convolution, one output-pixel parity class at a time: pixels h = s*i + a receive only
-    the taps r = r0 + s*j, r0 = (a + pad) mod s, from dy rows i + e - j, e = (a + pad) // s.  As a stride-1 correlation over
-    dy with tap u = J - 1 - j:  dy row = i - pad_lo + u,  pad_lo = J - 1 - e,  filter row = r0 + s * (J - 1 - u).
-    Returns [(a, r0, J, pad_lo)] for a in range(s); J == 0: the class receives nothing (dx = 0 there)."""
-    out = []
-    for a in range(stride):
-        r0 = (a + pad) % stride
-        J = max(0, -(-(K - r0) // stride))
-        out.append((a, r0, J, J - 1 - (a + pad) // stride))
-    return out
 
 
 def _nhwc_rows(x):
@@ -93,35 +79,6 @@ def _nhwc_rows(x):
     if x.stride() == (H * W * C, 1, W * C, C) or (C == 1 and x.is_contiguous()):
         return x.as_strided((B * H * W, C), (C, 1), x.storage_offset())
     return None
-
-
-def _dgrad_by_parity(dy2, weight, xshape, out_hw, stride, padding, exp, man, kahan, k_slice, om):
-    """dx of a strided convolution WITHOUT the zero-upsampled im2col matrix (3/4 of whose entries are zeros at stride 2):
-    each of the stride^2 output-pixel parity classes is a small stride-1 implicit GEMM over dy with the taps that reach
-    it (1, 2, 2 and 4 of the 9 taps for 3x3 / stride 2 / pad 1) and scatters its rows straight into dx.  Returns
-    (dx as [B*H*W, C], the operand-dtype copy of dy for the weight gradient)."""
-    B, C, H, W = xshape
-    OH, OW = out_hw
-    O, _, KH, KW = weight.shape
-    ws = weight.stride()
-    rows, cols = _parity_classes(KH, stride, padding), _parity_classes(KW, stride, padding)
-    live = [(ra, ca) for ra in rows for ca in cols if ra[2] > 0 and ca[2] > 0 and ra[0] < H and ca[0] < W]
-    full = len(live) == len([1 for ra in rows for ca in cols if ra[0] < H and ca[0] < W])
-    dx = (torch.empty if full else torch.zeros)(B * H * W, C, dtype=torch.float32, device=dy2.device)
-    specs = [native.spec_matrix(dy2, om)]
-    for (a, r0, Jr, _), (b, t0, Jt, _) in live:             # filter of the class: taps in REVERSED order, [C, (u, v, o)]
-        base = (r0 + stride * (Jr - 1)) * ws[2] + (t0 + stride * (Jt - 1)) * ws[3]
-        specs.append(native.spec_gather(weight, C, (Jr, Jt, O), (-stride * ws[2], -stride * ws[3], ws[0]), ws[1], om, base=base))
-    staged = []
-    for i in range(0, len(specs), 2):                       # two operands per staging launch
-        r = native.stage(*specs[i:i + 2])
-        staged += list(r) if isinstance(r, tuple) else [r]
-    dy_cast = staged[0]
-    for ((a, r0, Jr, plo_h), (b, t0, Jt, plo_w)), bt in zip(live, staged[1:]):
-        Ha, Wb = -(-(H - a) // stride), -(-(W - b) // stride)
-        native.gemm_conv(dy_cast.view(B, OH, OW, O), bt, Jr, Jt, (Ha, Wb), 1, (plo_h, plo_w), 1, exp, man, kahan, k_slice, om,
-                         variant=native.GEMM_1CTA, out=dx, scatter=(stride, a, b, H, W))
-    return dx, dy_cast
 
 
 class Quant_ConvTileFunction(Function):
@@ -196,10 +153,6 @@ class Quant_ConvTileFunction(Function):
                 dy_cast, bt = native.stage(native.spec_matrix(dy2, om), wspec)    # stride-1 data gradient = a convolution of dy
                 g = native.gemm_conv(dy_cast.view(B, OH, OW, O), bt, KH, KW, (H, W), 1, pad_t, dilation, exp, man, kahan, k_slice, om,
                                      splits=dsplits)
-            elif (dy2 is not None and _IMPLICIT and _PARITY and stride > 1 and dilation == 1 and C % 4 == 0 and
-                  native.conv_implicit_ok(O, KH, KW, 1, 0, 1, om) and
-                  all(J == 0 or 0 <= plo <= 127 for (_, _, J, plo) in _parity_classes(KH, stride, padding))):
-                g, dy_cast = _dgrad_by_parity(dy2, weight, (B, C, H, W), (OH, OW), stride, padding, exp, man, kahan, k_slice, om)
             else:
                 a, bt = native.stage(native.spec_im2col(dy, KH, KW, (H, W), 1, pad_t, dilation, om, in_dil=stride), wspec)   # [(b,h,w), (kh,kw,o)]
                 g = native.gemm_tc(a, bt, exp, man, kahan, k_slice, om, None, k=KH * KW * O, splits=dsplits)   # [(b,h,w), c] == NHWC
