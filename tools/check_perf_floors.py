@@ -90,7 +90,8 @@ def checks(prof):
                 floor("ResNet-18 8 GPUs: ours / unmodified reference (images/s)", j8["value"] / _bench_line(ref8)["value"], 5.0)
     del b1
     # ---- round 2 evidence -------------------------------------------------------------------------------------------
-    sw2 = sorted(glob.glob(os.path.join(prof, "allreduce_r2t*_n8_check_default.json")))
+    sw2 = [p for p in sorted(glob.glob(os.path.join(prof, "allreduce_r2t*_n8_check_default.json")))
+           if "stress_all_pass" in json.load(open(p))]                  # (the final sweep-only report is checked further down)
     if sw2:
         d = json.load(open(sw2[-1]))
         floor("r2 8-GPU all-reduce: correctness + stress + fault injection all pass",
@@ -123,6 +124,42 @@ def checks(prof):
     o8 = r2bench("r2t5_n8_bench_ours_resnet18.json")
     if o8 and o1:
         floor("r2 ResNet-18 weak scaling 1 -> 8 GPUs (ms/step ratio; both with the shipped defaults)", 6.768 / o8["ms_per_step"], 0.96)
+    # ---- final tree of round 2 (trips 9-14) ---------------------------------------------------------------------------
+    def r2file(rel):
+        p = os.path.join(prof, rel)
+        return _bench_line(p) if os.path.isfile(p) else None
+    refs = {"resnet18": r2bench("r2t4_bench_ref_resnet18.json"), "resnet50": r2bench("r2t4_bench_ref_resnet50.json"),
+            "davidnet": r2bench("r2t4_bench_ref_davidnet.json"), "resnet18_quant": qr}
+    lo_ratio = {"resnet18": 5.0, "resnet50": 7.5, "davidnet": 2.8, "resnet18_quant": 1200.0}
+    for cfg in ("resnet18", "resnet50", "davidnet", "resnet18_quant"):
+        f1, f8 = r2file(f"r2/t14_bench_{cfg}_n1.json"), r2bench(f"r2t13_n8_bench_ours_{cfg}.json")
+        if f1 and refs.get(cfg):
+            floor(f"r2 final {cfg} 1 GPU: ours e2e / unmodified reference", f1["e2e"]["value"] / refs[cfg]["value"], lo_ratio[cfg])
+        if f1 and f8:
+            floor(f"r2 final {cfg}: weak-scaling efficiency 1 -> 8 GPUs (device-timed)", f8["value"] / (8 * f1["value"]), 0.94)
+            floor(f"r2 final {cfg} 8 GPUs: end-to-end / device-timed throughput", f8["e2e"]["value"] / f8["value"], 0.97)
+    g9 = os.path.join(prof, "r2", "t9_bench_gemm_persistent_raster.json")
+    if os.path.isfile(g9):
+        tc = [r for r in json.load(open(g9))["gemm_tc"] if r.get("M") == 8192]
+        cub = [r["cublas_TFLOPs"] for r in tc if "cublas_TFLOPs" in r]
+        pair = [r["TFLOPs"] for r in tc if r.get("variant") == "2cta_256x256" and r.get("k_slice") == 8192]
+        one = [r["TFLOPs"] for r in tc if r.get("variant") == "1cta_128x128" and r.get("k_slice") == 8192 and r.get("acc") == [5, 10]]
+        if cub and pair and one:
+            floor("r2 final tcgen05 pair GEMM 8192^3 bf16, (5,10) cast at the end: fraction of cuBLAS bf16", pair[0] / cub[0], 0.85)
+            floor("r2 final tcgen05 128x128 GEMM 8192^3 bf16: fraction of cuBLAS bf16", one[0] / cub[0], 0.55)
+    qs, qi = r2file("r2/t9_bench_quant_staged.json"), r2file("r2/t14_bench_resnet18_quant_n1.json")
+    if qs and qi:
+        floor("r2 final Quant_Conv ResNet-18: implicit-GEMM step / staged-im2col step (throughput ratio)", qi["value"] / qs["value"], 1.3)
+    for n, name in ((8, "allreduce_r2t13_n8_check_default.json"), (4, "allreduce_r2t5_n4_check_default.json")):
+        pth = os.path.join(prof, name)
+        if not os.path.isfile(pth):
+            continue
+        d = json.load(open(pth))
+        floor(f"r2 final {n}-GPU all-reduce: every correctness case passes", 1.0 if d.get("correct_all_pass") else 0.0, 1.0)
+        for r in d["sweep"]:
+            nb, auto, nccl = r["fp32_bytes"], r["fused_auto_us"], r["nccl_fp32_allreduce_us"]
+            lo = (1.0 if nb <= (1 << 20) else 1.4) if n == 8 else (0.9 if nb <= (1 << 20) else 1.35)
+            floor(f"r2 final {n}-GPU all-reduce {nb} B: NCCL fp32 time / fused AUTO time", nccl / auto, lo)
     return out
 
 
