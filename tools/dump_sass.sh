@@ -24,6 +24,11 @@ pick = {
  'gemm_tcgen05_2cta_kernel_bf16_f16acc': r'gemm_tcgen05_2cta_kernelILi0ENS_3tc26AccF16ELb0',
  'gemm_tcgen05_mx_kernel': r'gemm_tcgen05_mx_kernelINS_8FmtHwF16ELb0',
  'mx_quantize_kernel': r'mx_quantize_kernelILb0',
+ 'operand_stage_kernel_bf16': r'operand_stage_kernelILi0E',
+ 'bn_stats_kernel': r'bn_stats_kernel',
+ 'bn_apply_kernel_relu_res': r'bn_apply_kernelILb1ELb1E',
+ 'bn_bwd_stats_kernel_relu': r'bn_bwd_stats_kernelILb1E',
+ 'bn_bwd_apply_kernel_relu_res': r'bn_bwd_apply_kernelILb1ELb1E',
  'allreduce_fused_kernel_e4m3': r'allreduce_fused_kernel.*FmtTILi4ELi3EEELi8ELb0',
  'allreduce_fused_kernel_e5m2_kahan': r'allreduce_fused_kernel.*FmtTILi5ELi2EEELi8ELb1',
 }
