@@ -75,6 +75,8 @@ def set_default_gemm_mode(mode: str) -> None:
     _DEFAULT_GEMM_MODE = mode
 
 
+_CPU_MODEL = True            # CPU tensors in tile mode take the CPU model (tests/test_stage_model_cpu.py turns it off to drive
+#                              the GPU path's descriptor logic with monkeypatched kernels)
 _TILE_MIN_WORK = 1 << 24      # M*N*K above which the tensor-core kernel takes over in mode="auto"
 
 
@@ -94,6 +96,8 @@ def operand_mode_for(exp: int, man: int, operands: Optional[str] = None) -> int:
 
 _OPERAND_NAME = {"bf16": native.OPERAND_BF16, "tf32": native.OPERAND_TF32, "e4m3": native.OPERAND_E4M3,
                  "e5m2": native.OPERAND_E5M2}
+_OPERAND_FORMAT = {native.OPERAND_BF16: (8, 7), native.OPERAND_TF32: (8, 10), native.OPERAND_E4M3: (4, 3),
+                   native.OPERAND_E5M2: (5, 2)}          # (exp, man) of each tensor-core operand type, for the CPU model
 
 
 def resolve_gemm_mode(mode: Optional[str], is_cuda: bool, work: int) -> str:
@@ -124,9 +128,16 @@ def tile_gemm(a_view: torch.Tensor, bt_view: torch.Tensor, exp: int, man: int, k
     om = operand_mode_for(exp, man, operands)
     M, K = a_view.shape
     N = bt_view.shape[0]
-    a_op, b_op = native.stage(native.spec_matrix(a_view, om), native.spec_matrix(bt_view, om))       # ONE launch, both operands
     if splits is None:
         splits = splits_for(M, N, K, k_slice)
+    if not a_view.is_cuda and _CPU_MODEL:
+        # CPU MODEL of the tensor-core semantics (slow; for tests and for reading the numerics without a GPU): operands
+        # rounded to the operand format, wide partial sums per K-slice, s = Q(s (+) Q(partial)) with IEEE rounding,
+        # split-K = ordered fold of the splits (csrc/cpu/cpu_ops.cpp::gemm_tile_cpu)
+        oe, om_ = _OPERAND_FORMAT[om]
+        out = native.gemm_tile_cpu(a_view.contiguous(), bt_view.t().contiguous(), exp, man, "ieee", bool(kahan), k_slice, oe, om_, splits)
+        return out + bias if bias is not None else out
+    a_op, b_op = native.stage(native.spec_matrix(a_view, om), native.spec_matrix(bt_view, om))       # ONE launch, both operands
     return native.gemm_tc(a_op, b_op, exp, man, bool(kahan), k_slice, om, bias, k=K, splits=splits)
 
 
@@ -144,6 +155,9 @@ def quant_gemm(a: torch.Tensor, b: torch.Tensor, man: int = 23, exp: int = 8, mo
         (4,3)/(5,2), bf16 for man<=7, tf32 otherwise — numerics differ from "exact" by design,
         which is why it is opt-in (``mode=``, ``set_default_gemm_mode``, env CPD_B200_GEMM_MODE).
         Operands are staged by one fused gather+cast launch each (no pad / transposed copies).
+        On CPU tensors the same semantics run through a (slow) C++ model - operands rounded to the operand format,
+        wide partial sums per K-slice, the same casts and split-K fold - so the numerics can be read and tested
+        without a GPU (tests/test_tile_mode_cpu.py); block-scaled operands have no CPU model.
     mode="auto":  exact on CPU and below 2^24 multiply-adds, tile otherwise.
     ``operands``: "bf16" | "tf32" | "e4m3" | "e5m2" | "mxe4m3" | "mxe5m2" (block-scaled fp8: one
     UE8M0 scale per 32 K-elements, tcgen05 kind::mxf8f6f4.block_scale); default by format.
@@ -160,8 +174,8 @@ def quant_gemm(a: torch.Tensor, b: torch.Tensor, man: int = 23, exp: int = 8, mo
         if bias is not None:
             out += bias
         return out
-    if not a.is_cuda:
-        raise NotImplementedError("mode='tile' needs a CUDA device (use ops.native.gemm_tile_cpu for the CPU model)")
+    if not a.is_cuda and operands in ("mxe4m3", "mxe5m2"):
+        raise NotImplementedError("block-scaled operands have no CPU model; use operands='e4m3' / 'e5m2' on the CPU")
     if operands in ("mxe4m3", "mxe5m2"):       # block-scaled fp8 operands (one power-of-two scale per 32 K-elements)
         e5 = operands == "mxe5m2"
         if K % 16:

@@ -14,6 +14,7 @@ from torch.nn.parameter import Parameter
 from .functional import (float_quantize, quant_gemm, quantizer, resolve_gemm_mode, operand_mode_for, splits_for,
                          tile_gemm)
 from ..ops import native
+from . import functional as _functional
 
 __all__ = ["Quantizer", "Quant_Linear", "Quant_Conv", "Quant_LinearFunction", "Quant_ConvTileFunction"]
 
@@ -81,6 +82,46 @@ def _nhwc_rows(x):
     return None
 
 
+def _cols_cpu(x, KH, KW, stride, padding, dilation):
+    """Explicit im2col matrix [B*OH*OW, (kh, kw, c)] - the CPU model's stand-in for what the GPU path reads through TMA."""
+    B, C = x.shape[:2]
+    cols = F.unfold(x.contiguous(), (KH, KW), dilation=dilation, padding=padding, stride=stride)        # [B, C*KH*KW, L]
+    L = cols.shape[-1]
+    return cols.view(B, C, KH * KW, L).permute(0, 3, 2, 1).reshape(B * L, KH * KW * C)
+
+
+def _conv_tile_cpu(x, weight, bias, exp, man, stride, padding, dilation, k_slice, operands, kahan, dy=None, needs=(True, True, True)):
+    """CPU MODEL of the tile-mode convolution (same three GEMMs, K orders, K-slices and split-K factors as the GPU
+    path, through ``tile_gemm``'s CPU model).  dy is None: forward, returns y; else returns (dx, dw, db)."""
+    B, C, H, W = x.shape
+    O, _, KH, KW = weight.shape
+    OH = (H + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
+    OW = (W + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
+    wmat = weight.permute(0, 2, 3, 1).reshape(O, KH * KW * C)                                      # [O, (kh, kw, c)]
+    if dy is None:
+        y = tile_gemm(_cols_cpu(x, KH, KW, stride, padding, dilation), wmat, exp, man, kahan, k_slice, operands, bias)
+        return y.view(B, OH, OW, O).permute(0, 3, 1, 2)
+    dx = dw = db = None
+    if needs[0]:                                            # transposed convolution: taps of the zero-upsampled dy x flipped filter
+        up = dy.new_zeros(B, O, (OH - 1) * stride + 1, (OW - 1) * stride + 1)
+        up[:, :, ::stride, ::stride] = dy
+        pad_t = dilation * (KH - 1) - padding
+        extra_h, extra_w = H - (up.shape[2] + 2 * pad_t - dilation * (KH - 1)), W - (up.shape[3] + 2 * pad_t - dilation * (KW - 1))
+        up = F.pad(up, (max(pad_t, 0), max(pad_t, 0) + extra_w, max(pad_t, 0), max(pad_t, 0) + extra_h))
+        if pad_t < 0:
+            up = up[:, :, -pad_t:up.shape[2] + pad_t, -pad_t:up.shape[3] + pad_t]
+        wflip = weight.flip(2, 3).permute(1, 2, 3, 0).reshape(C, KH * KW * O)                      # [C, (kh, kw, o)]
+        g = tile_gemm(_cols_cpu(up, KH, KW, 1, 0, dilation), wflip, exp, man, kahan, k_slice, operands)
+        dx = g.view(B, H, W, C).permute(0, 3, 1, 2)
+    if needs[1]:
+        dyt = dy.permute(1, 0, 2, 3).reshape(O, B * OH * OW)                                       # [O, pixels]
+        g = tile_gemm(dyt, _cols_cpu(x, KH, KW, stride, padding, dilation).t(), exp, man, kahan, k_slice, operands)
+        dw = g.view(O, KH, KW, C).permute(0, 3, 1, 2)
+    if bias is not None and needs[2]:
+        db = float_quantize(dy.sum((0, 2, 3)), exp, man)
+    return dx, dw, db
+
+
 class Quant_ConvTileFunction(Function):
     """2-D convolution whose three GEMMs run on the tensor cores with the accumulator at (exp, man), WITHOUT the
     reference's glue (quant_module.py:115-139: F.unfold's fp32 column matrix, transposed copies, separate bias add and
@@ -110,6 +151,11 @@ class Quant_ConvTileFunction(Function):
         O, _, KH, KW = weight.shape
         OH = (H + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
         OW = (W + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
+        if not x.is_cuda and _functional._CPU_MODEL:         # CPU model of the same three GEMMs
+            ctx.save_for_backward(x, weight)
+            ctx.cpu = (exp, man, stride, padding, dilation, k_slice, operands, kahan, bias)
+            return _conv_tile_cpu(x, weight, bias, exp, man, stride, padding, dilation, k_slice, operands, kahan)
+        ctx.cpu = None
         om = operand_mode_for(exp, man, operands)
         ws = weight.stride()
         wspec = native.spec_gather(weight, O, (KH, KW, C), (ws[2], ws[3], ws[1]), ws[0], om)
@@ -134,6 +180,11 @@ class Quant_ConvTileFunction(Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
+        if ctx.cpu is not None:
+            exp, man, stride, padding, dilation, k_slice, operands, kahan, bias = ctx.cpu
+            dx, dw, db = _conv_tile_cpu(x, weight, bias, exp, man, stride, padding, dilation, k_slice, operands, kahan, dy=dy,
+                                        needs=ctx.needs_input_grad[:3])
+            return dx, dw, db, None, None, None, None, None, None, None, None
         exp, man, stride, padding, dilation, k_slice, om, kahan, has_bias, (OH, OW), x_is_cast, (B, C, H, W) = ctx.cfg
         O, _, KH, KW = weight.shape
         dx = dw = db = None

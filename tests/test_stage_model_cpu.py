@@ -83,6 +83,8 @@ def _gemm_tc(a, bt, exp, man, kahan=False, k_slice=128, operand_mode=0, bias=Non
 
 @pytest.fixture
 def cpu_model(monkeypatch):
+    from cpd_b200.quant import functional as qfn
+    monkeypatch.setattr(qfn, "_CPU_MODEL", False)            # drive the GPU path's descriptor logic, not the CPU model
     monkeypatch.setattr(native, "spec_gather", _gather)
     monkeypatch.setattr(native, "spec_matrix", _matrix)
     monkeypatch.setattr(native, "spec_im2col", _im2col)
