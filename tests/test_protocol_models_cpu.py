@@ -1,4 +1,4 @@
-"""Executable models of two device-side protocols, run under random interleavings (no GPU):
+"""Executable models of three device-side protocols, run under random interleavings (no GPU):
 
 1. the persistent tcgen05 GEMM pipeline (gemm_tcgen05_sm100a.cu / gemm_tcgen05_2cta_sm100a.cu): TMA producer, MMA
    issuer and requant epilogue with RUNNING stage / phase counters across tiles, mbarrier parity semantics,
@@ -7,6 +7,9 @@
    it, every tile's slices are consumed in order.
 2. the two-level arrival / re-arming protocol of the BatchNorm statistics kernels (bn_act_sm100.cu::arrive_and_reduce):
    exactly one CTA per launch finalises, it sees every group partial, all counters return to zero for the next launch.
+3. the cross-GPU epoch-flag protocol of the fused all-reduce (allreduce_fused_sm100a.cu): flags that are never cleared,
+   parity-indexed buffers, no trailing barrier, variants interleaving from launch to launch, ranks running at their own
+   pace - no read ever sees stale or already-overwritten data (and with a single buffer it does: the model is not vacuous).
 
 The models restate the kernels' index arithmetic (it % NUM_STAGES, (it / NUM_STAGES) & 1, sl_run % NUM_ACC, ...), so an
 off-by-one in a phase bit or a wait on the wrong parity shows up here as a deadlock or an invariant violation."""
@@ -199,3 +202,75 @@ def test_bn_two_level_arrival_has_one_finaliser_and_rearms(slabs):
         assert len(fin) == 1, fin
         assert all(fin[0][1]), "the finaliser ran before every group partial was written"
         assert not any(counters), counters
+
+
+def run_allreduce_epochs(W, variants, rng, double_buffered=True):
+    """The cross-GPU flag protocol of allreduce_fused_sm100a.cu ("Why the protocol is safe without a trailing
+    barrier or host resets"): monotonic epoch flags that are never cleared, buffers indexed by epoch parity, no barrier at
+    the end of a launch.  Every rank runs the launches back to back at its own pace; every read asserts that it sees the
+    value its producer wrote IN THIS LAUNCH (not a stale one, not one already overwritten by a rank that ran ahead)."""
+    par = (lambda e: e & 1) if double_buffered else (lambda e: 0)
+    flags = [[[0] * W for _ in range(W)] for _ in range(3)]           # flags[phase][dst][src] = epoch of src's last signal
+    mailbox = [[None, None] for _ in range(W)]                        # mailbox[rank][parity]   (pulled by the peers)
+    data = [[None, None] for _ in range(W)]                           # wire buffer of a rank   (pulled by the peers)
+    gather = [[[None] * W for _ in range(2)] for _ in range(W)]       # gather[dst][parity][src] (pushed by the owners)
+
+    def rank(me):
+        peers = [p for p in range(W) if p != me]
+        for e, v in enumerate(variants, start=1):
+            p = par(e)
+            phases = ([] if v == "raw" else [0]) + [1]
+            for ph in phases:
+                buf = mailbox if ph == 0 else data
+                buf[me][p] = (me, e)
+                yield
+                for q in peers:                                      # st.release.sys flag[peer][phase][me] = epoch
+                    flags[ph][q][me] = e
+                    yield
+                for q in peers:                                      # ld.acquire.sys until the peer's epoch arrived
+                    while flags[ph][me][q] - e < 0:
+                        yield
+                for q in peers:
+                    assert buf[q][p] == (q, e), f"rank {me} launch {e} phase {ph}: read {buf[q][p]} from rank {q}"
+                    yield
+            if v == "twoshot":
+                for q in peers:                                      # push my reduced chunk into every peer's gather buffer
+                    gather[q][p][me] = (me, e)
+                    yield
+                for q in peers:
+                    flags[2][q][me] = e
+                    yield
+                for q in peers:
+                    while flags[2][me][q] - e < 0:
+                        yield
+                for q in peers:
+                    assert gather[me][p][q] == (q, e), f"rank {me} launch {e} gather: read {gather[me][p][q]} from rank {q}"
+                    yield
+
+    actors = [rank(r) for r in range(W)]
+    alive = list(range(W))
+    for _ in range(1000000):
+        if not alive:
+            return
+        c = rng.choice(alive)
+        try:
+            next(actors[c])
+        except StopIteration:
+            alive.remove(c)
+    raise AssertionError(f"deadlock: ranks {alive} never finished")
+
+
+@pytest.mark.parametrize("W", [2, 3, 4, 8])
+def test_allreduce_epoch_flags_never_show_stale_or_overwritten_data(W):
+    rng = random.Random(W)
+    for trial in range(60 if W <= 4 else 10):
+        variants = [rng.choice(["raw", "oneshot", "twoshot"]) for _ in range(7)]       # variants interleave freely
+        run_allreduce_epochs(W, variants, rng)
+
+
+def test_allreduce_model_needs_the_double_buffering():
+    """Not vacuous: with ONE buffer per rank a rank that runs ahead overwrites data a slow peer has not read yet."""
+    rng = random.Random(7)
+    with pytest.raises(AssertionError):
+        for trial in range(200):
+            run_allreduce_epochs(3, ["raw"] * 6, rng, double_buffered=False)
