@@ -88,3 +88,16 @@ def test_fcn_d8_topology():
         h.remove()
     assert y.shape == (1, 19, 129, 129)
     assert feats == [33, 17, 17, 17]                                   # output stride 8: stages 3 and 4 dilate instead of striding
+
+
+@pytest.mark.timeout(900)
+def test_fcn_trainer_two_gloo_ranks(tmp_path):
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = _run(["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+                os.path.join(ROOT, "examples/FCN/train_fcn.py"), "--cpu", "--arch", "fcn_r18_d8", "--width", "8", "--crop", "65",
+                "--batch-size", "2", "--max-iters", "4", "--dataset-len", "8", "--val-len", "4", "--val-freq", "4", "--print-freq", "2",
+                "--workers", "0", "--use_APS"], str(tmp_path))
+    assert "batch 2 x 2" in out and "Iter [4/4]" in out and " * Iter 4: mIoU" in out and "nan" not in out.lower()
