@@ -15,7 +15,6 @@ from typing import Dict, List, Sequence, Tuple
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 
 class Scale(nn.Module):

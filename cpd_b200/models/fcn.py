@@ -4,7 +4,6 @@ last two stages trade their strides for dilations 2 and 4 (output stride 8), an 
 dropout -> 1x1 classifier) on stage 4, the auxiliary head on stage 3, logits upsampled bilinearly to the input size."""
 from __future__ import annotations
 
-import torch
 import torch.nn as nn
 import torch.nn.functional as F
 

@@ -5,7 +5,6 @@ the same parameters, buffers and arithmetic with the ReLU and the shortcut add f
 channels_last fp32 CUDA tensors (stock ops everywhere else)."""
 from __future__ import annotations
 
-import torch
 import torch.nn as nn
 import torch.nn.functional as F
 

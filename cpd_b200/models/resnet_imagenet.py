@@ -3,7 +3,6 @@ example/ResNet50/main.py:67).  Own implementation with the same topology and
 initialisation; resnet50: 161 parameter tensors, 25 557 032 parameters."""
 from __future__ import annotations
 
-import torch
 import torch.nn as nn
 import torch.nn.functional as F
 

@@ -9,7 +9,7 @@ per-tensor weight-decay multipliers (ResNet-50 recipe: no decay on BN, main.py:1
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import time
 from collections import deque
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.distributed as dist

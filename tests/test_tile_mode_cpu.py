@@ -6,7 +6,6 @@ import torch
 import torch.nn.functional as F
 
 from cpd_b200 import Quant_Conv, Quant_Linear, float_quantize, quant_gemm
-from cpd_b200.ops import native
 
 
 def _bf(t):
