@@ -135,3 +135,66 @@ def test_tile_linear_descriptors_reproduce_matmul(cpu_model):
     assert torch.allclose(x.grad, dy @ lin.weight.detach(), rtol=1e-5, atol=1e-5)
     assert torch.allclose(lin.weight.grad, dy.t() @ x.detach(), rtol=1e-5, atol=1e-5)
     assert torch.allclose(lin.bias.grad, dy.sum(0), rtol=1e-5, atol=1e-5)
+
+
+def _gemm_conv_model(x_nhwc, bt, kh, kw, out_hw, stride, pad, dil, exp, man, kahan=False, k_slice=128, operand_mode=0, bias=None,
+                     variant=0, splits=1):
+    """native.gemm_conv as a torch convolution: x [B,H,W,C], bt [O, (kh,kw,c)] -> [B*OH*OW, O]."""
+    B, H, W, C = x_nhwc.shape
+    O = bt.shape[0]
+    w = bt[:, :kh * kw * C].reshape(O, kh, kw, C).permute(0, 3, 1, 2)
+    y = F.conv2d(x_nhwc.permute(0, 3, 1, 2).double(), w.double(), None if bias is None else bias.detach().double(), stride=stride,
+                 padding=pad, dilation=dil)
+    assert tuple(y.shape[-2:]) == tuple(out_hw)
+    return y.permute(0, 2, 3, 1).reshape(-1, O).float()
+
+
+def _gemm_wgrad_model(dy_rows, x_nhwc, kh, kw, out_hw, stride, pad, dil, exp, man, kahan=False, k_slice=128, splits=1, _lbo=0, _sbo=0):
+    """native.gemm_wgrad: dW [O, (kh,kw,c)] = sum_pixels dy[pixel, o] * x-tap[pixel, (kh,kw,c)]."""
+    B, H, W, C = x_nhwc.shape
+    O = dy_rows.shape[1]
+    cols = F.unfold(x_nhwc.permute(0, 3, 1, 2).double(), (kh, kw), dilation=dil, padding=pad, stride=stride)       # [B, C*kh*kw, L]
+    L = cols.shape[-1]
+    cols = cols.view(B, C, kh * kw, L).permute(0, 3, 2, 1).reshape(B * L, kh * kw * C)
+    assert dy_rows.shape[0] == B * L and dy_rows.is_contiguous() and x_nhwc.is_contiguous()
+    return (dy_rows.double().t() @ cols).float()
+
+
+@pytest.mark.parametrize("dy_kind", ["like", "nchw", "expanded"])
+@pytest.mark.parametrize("cfg", [(8, 12, 3, 1, 1, 1), (8, 8, 3, 2, 1, 1), (8, 16, 1, 2, 0, 1), (8, 8, 3, 1, 2, 2), (8, 12, 5, 1, 2, 1)])
+def test_implicit_conv_glue_reproduces_conv2d_forward_and_backward(cpu_model, monkeypatch, cfg, dy_kind):
+    """The IMPLICIT-GEMM branch of Quant_ConvTileFunction (cast-only staging, the bf16 x kept for backward, dy cast shared by
+    the data- and weight-gradient GEMMs, staged fallback for the strided data gradient, a non-channels_last dy) with
+    native.gemm_conv / gemm_wgrad replaced by torch models of what the kernels compute."""
+    cin, cout, k, stride, pad, dil = cfg
+    calls = {"conv": 0, "wgrad": 0}
+
+    def conv_model(*a, **kw):
+        calls["conv"] += 1
+        return _gemm_conv_model(*a, **kw)
+
+    def wgrad_model(*a, **kw):
+        calls["wgrad"] += 1
+        return _gemm_wgrad_model(*a, **kw)
+
+    monkeypatch.setattr(native, "conv_implicit_ok", lambda *a, **kw: True)
+    monkeypatch.setattr(native, "gemm_conv", conv_model)
+    monkeypatch.setattr(native, "gemm_wgrad", wgrad_model)
+    torch.manual_seed(cin + k)
+    conv = Quant_Conv(cin, cout, k, stride=stride, padding=pad, dilation=dil, bias=True, exp=8, man=23, mode="tile", operands="bf16")
+    conv = conv.to(memory_format=torch.channels_last)
+    x = torch.randn(3, cin, 10, 9).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = conv(x)
+    xr = x.detach().clone().requires_grad_(True)
+    wr = conv.weight.detach().clone().requires_grad_(True)
+    br = conv.bias.detach().clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, stride=stride, padding=pad, dilation=dil)
+    assert torch.allclose(y, yr, rtol=1e-5, atol=1e-5) and calls["conv"] == 1
+    dy = {"like": torch.randn_like(y), "nchw": torch.randn(yr.shape), "expanded": torch.ones(1).expand_as(yr)}[dy_kind]
+    y.backward(dy)
+    yr.backward(dy)
+    assert torch.allclose(x.grad, xr.grad, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(conv.weight.grad, wr.grad, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(conv.bias.grad, br.grad, rtol=1e-4, atol=1e-4)
+    assert calls["wgrad"] == (1 if cout % 8 == 0 else 0)               # O * 2 bytes must be a multiple of 16 for dy's tensor map
+    assert calls["conv"] == (2 if stride == 1 else 1)                  # strided data gradient: staged zero-upsampled path
