@@ -109,6 +109,26 @@ def resolve_gemm_mode(mode: Optional[str], is_cuda: bool, work: int) -> str:
     return mode
 
 
+def mx_round(x: torch.Tensor, e5m2: bool = False) -> torch.Tensor:
+    """What a block-scaled (MXFP8) operand is worth to the tensor core, as fp32: per 32 consecutive K-elements of a row
+    one power-of-two scale 2^e, e = ceil(log2(max|x| / max finite code)) (the smallest that avoids saturation - APS per
+    block instead of per tensor), values rounded to fp8 after the scaling.  Torch model of mx_quantize_sm100.cu (any
+    device); the CUDA kernel additionally emits the codes and the UE8M0 scales in the tcgen05 scale-factor layout."""
+    if x.dim() != 2:
+        raise ValueError("mx_round: 2-D tensor expected")
+    R, K = x.shape
+    Kp = (K + 31) // 32 * 32
+    xb = torch.nn.functional.pad(x.float(), (0, Kp - K)).view(R, Kp // 32, 32)
+    max_code = 57344.0 if e5m2 else 448.0
+    amax = xb.abs().amax(-1, keepdim=True)
+    mant, ex = torch.frexp(amax / max_code)                        # q = mant * 2^ex, mant in [0.5, 1)
+    e = torch.where(mant == 0.5, ex - 1, ex).clamp(-127, 127)       # ceil(log2 q)
+    e = torch.where((amax > 0) & torch.isfinite(amax), e, torch.full_like(e, -127))
+    scale = torch.ldexp(torch.ones_like(amax), e)
+    codes = (xb / scale).clamp(-max_code, max_code).to(torch.float8_e5m2 if e5m2 else torch.float8_e4m3fn).float()
+    return (codes * scale).view(R, Kp)[:, :K].contiguous()
+
+
 def splits_for(M: int, N: int, K: int, k_slice: int) -> int:
     """Split-K factor of the tile mode: skinny outputs with a long reduction (weight gradients: [out_ch, taps] over
     batch x pixels) get enough K ranges to fill the 148 SMs; each split keeps >= 4 K-slices."""
@@ -157,7 +177,8 @@ def quant_gemm(a: torch.Tensor, b: torch.Tensor, man: int = 23, exp: int = 8, mo
         Operands are staged by one fused gather+cast launch each (no pad / transposed copies).
         On CPU tensors the same semantics run through a (slow) C++ model - operands rounded to the operand format,
         wide partial sums per K-slice, the same casts and split-K fold - so the numerics can be read and tested
-        without a GPU (tests/test_tile_mode_cpu.py); block-scaled operands have no CPU model.
+        without a GPU (tests/test_tile_mode_cpu.py); block-scaled operands go through ``mx_round``, the torch model of the
+        MXFP8 staging kernel.
     mode="auto":  exact on CPU and below 2^24 multiply-adds, tile otherwise.
     ``operands``: "bf16" | "tf32" | "e4m3" | "e5m2" | "mxe4m3" | "mxe5m2" (block-scaled fp8: one
     UE8M0 scale per 32 K-elements, tcgen05 kind::mxf8f6f4.block_scale); default by format.
@@ -175,7 +196,11 @@ def quant_gemm(a: torch.Tensor, b: torch.Tensor, man: int = 23, exp: int = 8, mo
             out += bias
         return out
     if not a.is_cuda and operands in ("mxe4m3", "mxe5m2"):
-        raise NotImplementedError("block-scaled operands have no CPU model; use operands='e4m3' / 'e5m2' on the CPU")
+        # CPU model: operands as the tensor core sees them (fp8 codes x their block's power-of-two scale), then the tile model
+        e5 = operands == "mxe5m2"
+        out = native.gemm_tile_cpu(mx_round(a, e5), mx_round(b.t(), e5).t().contiguous(), exp, man, "ieee",
+                                   bool(kahan) if kahan is not None else False, k_slice)
+        return out + bias if bias is not None else out
     if operands in ("mxe4m3", "mxe5m2"):       # block-scaled fp8 operands (one power-of-two scale per 32 K-elements)
         e5 = operands == "mxe5m2"
         if K % 16:

@@ -75,6 +75,32 @@ def test_tile_conv_cpu_low_precision_accumulator_stays_in_format():
     assert torch.equal(y, float_quantize(y, 4, 3, "ieee"))                  # every output is a member of (4,3)
 
 
-def test_block_scaled_operands_have_no_cpu_model():
-    with pytest.raises(NotImplementedError):
-        quant_gemm(torch.randn(4, 32), torch.randn(32, 4), man=10, exp=5, mode="tile", operands="mxe4m3")
+@pytest.mark.parametrize("e5m2", [False, True])
+def test_block_scaled_operand_model(e5m2):
+    """mx_round: power-of-two scale per 32 K-elements chosen so that the block's maximum just fits the fp8 range; blocks of
+    very different magnitude keep their relative precision (what a per-tensor fp8 cast cannot do)."""
+    from cpd_b200.quant.functional import mx_round
+    torch.manual_seed(5)
+    x = torch.randn(6, 100) * torch.logspace(-6, 6, 100 // 25 * 25 + 0, base=10.0)[:100].roll(3)
+    x[0, :32] = 0.0                                                   # an all-zero block
+    y = mx_round(x, e5m2)
+    assert y.shape == x.shape and torch.equal(y[0, :32], torch.zeros(32))
+    rel = 2.0 ** -(2 if e5m2 else 3)                                   # half an ulp of the block maximum's binade, relative
+    xb, yb = torch.nn.functional.pad(x, (0, 28)).view(6, 4, 32), torch.nn.functional.pad(y, (0, 28)).view(6, 4, 32)
+    amax = xb.abs().amax(-1, keepdim=True)
+    assert ((xb - yb).abs() <= rel * amax).all()                      # error bounded relative to the BLOCK maximum
+    assert torch.equal(mx_round(y, e5m2), y)                          # idempotent
+    max_code = 57344.0 if e5m2 else 448.0
+    ratio = yb.abs().amax(-1) / amax.squeeze(-1).clamp_min(1e-30)     # the maximum survives (no saturation, no underflow)
+    assert ((ratio > 0.9) | (amax.squeeze(-1) == 0)).all() and max_code > 0
+
+
+def test_block_scaled_tile_gemm_cpu():
+    torch.manual_seed(6)
+    a, b = torch.randn(9, 96) * 100.0, torch.randn(96, 7) * 1e-3
+    from cpd_b200.quant.functional import mx_round
+    c = quant_gemm(a, b, man=23, exp=8, mode="tile", operands="mxe4m3")
+    ref = (mx_round(a).double() @ mx_round(b.t()).t().double()).float()
+    assert (c - ref).abs().max() <= 2e-6 * ref.abs().max()
+    plain = a @ b
+    assert (c - plain).abs().max() <= 0.08 * plain.abs().max()       # fp8 operands: a few percent
