@@ -166,6 +166,30 @@ int main() {
     }
   }
 
+  // ---- split-K of the tile model == the ordered quantised fold of the splits' own tile GEMMs ----
+  {
+    const int M = 5, N = 6, K = 100, ks = 16;                       // 7 slices -> 3 splits of 3, 3, 1 slices
+    std::vector<float> A((size_t)M * K), Bt((size_t)N * K), C((size_t)M * N), P((size_t)M * N), S((size_t)M * N), T((size_t)M * N);
+    std::uniform_real_distribution<float> u(-1.f, 1.f);
+    for (auto& t : A) t = u(rng);
+    for (auto& t : Bt) t = u(rng);
+    for (auto& f : {std::pair<int, int>{5, 10}, {4, 3}, {8, 23}}) {
+      cpd::gemm_tile_cpu(A.data(), K, 1, Bt.data(), 1, K, C.data(), N, M, N, K, f.first, f.second, 1, false, ks, 8, 7, 3);
+      std::fill(S.begin(), S.end(), 0.f);
+      const int k_per_split = 3 * ks;
+      for (int k0 = 0; k0 < K; k0 += k_per_split) {
+        const int kz = std::min(k_per_split, K - k0);
+        cpd::gemm_tile_cpu(A.data() + k0, K, 1, Bt.data() + k0, 1, K, P.data(), N, M, N, kz, f.first, f.second, 1, false, ks, 8, 7, 1);
+        for (size_t i = 0; i < S.size(); ++i) T[i] = S[i] + P[i];
+        cpd::quantize_cpu(T.data(), S.data(), (int64_t)S.size(), f.first, f.second, 1);               // s = Q(s + part), IEEE
+      }
+      for (size_t i = 0; i < C.size(); ++i) CHECK(same(C[i], S[i]), "split-K tile GEMM != ordered fold of the splits at %zu: %a vs %a", i, C[i], S[i]);
+      cpd::gemm_tile_cpu(A.data(), K, 1, Bt.data(), 1, K, P.data(), N, M, N, K, f.first, f.second, 1, false, ks, 8, 7, 64);   // more splits than slices
+      cpd::gemm_tile_cpu(A.data(), K, 1, Bt.data(), 1, K, T.data(), N, M, N, K, f.first, f.second, 1, false, ks, 8, 7, 7);
+      for (size_t i = 0; i < C.size(); ++i) CHECK(same(P[i], T[i]), "splits > slices must clamp to one slice per split at %zu", i);
+    }
+  }
+
   // ---- APS fold: W ranks, several tensors incl. all-zero / Inf / denormal ones; fp32 identity == plain sum ----
   {
     const int T = 5, W = 4;
